@@ -1,0 +1,879 @@
+// Engine: host-side table builder, device memory, launch logic and the C-ABI (include/chimp_b200.h).
+//
+// The builder turns the reference's tables (Grid::neigList_, bulk list, bounce-back / link
+// lists, MonLatMpi exchange lists) into the pull table T described in kernels.cuh by
+// symbolically replaying one reference iteration:
+//   1. push      fTmp(q, neighbor(q,n)) = f*_q(n) for bulk n in order     (LBfield.h:350-357)
+//   2. exchange  real(q) <- ghost(q) of the neighbour rank                 (LBmonlatmpi.h:236-297)
+//   3. boundary copies in the order the main applies them                  (LBhalfwaybb.h:37-63,
+//                                                                           std_one_phase/main.cpp:138-203)
+// Every slot of the reference's f array carries a symbolic source (which own node's
+// post-collision value, in which orientation, or which halo element); sequential replay
+// reproduces last-writer-wins and chained copies exactly.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/chimp_b200.h"
+#include "kernels.cuh"
+
+namespace chimp {
+__global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint32_t *, int *);
+__global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *);
+} // namespace chimp
+
+using namespace chimp;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CUDA_OK(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct LatInfo { int nQ, nD, nPairs; };
+LatInfo latInfo(int id)
+{
+    switch (id) {
+    case CHIMP_D2Q9: return {D2Q9::nQ, D2Q9::nD, D2Q9::nPairs};
+    case CHIMP_D3Q19: return {D3Q19::nQ, D3Q19::nD, D3Q19::nPairs};
+    case CHIMP_D3Q27: return {D3Q27::nQ, D3Q27::nD, D3Q27::nPairs};
+    }
+    return {0, 0, 0};
+}
+int revDir(const LatInfo &li, int q) { return q == li.nQ - 1 ? q : (q + li.nPairs) % (li.nQ - 1); }
+
+struct Op { int kind, dn, dq, sn, sq; }; // kind 0 copy, 1 anti bounce back, 2 swap
+
+struct Neighbor {
+    int rank = -1;
+    std::vector<int32_t> sendNodes, nDirSend, dirSend, recvNodes, nDirRecv, dirRecv;
+    long long sendCount = 0, recvCount = 0; // per field
+    long long *d_sendSrc = nullptr, *d_recvDst = nullptr;
+    double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
+};
+
+template <class T>
+void freeDev(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+} // namespace
+
+struct chimp_lattice {
+    int lattice = 0;
+    LatInfo li{};
+    int device = 0;
+    int nFields = 1;
+    // host-side inputs (released by finalize)
+    int nNodes = 0;
+    std::vector<int32_t> neigh, bulk;
+    std::vector<Op> ops;
+    std::vector<Neighbor> nbrs;
+    std::vector<int32_t> solidBnd;
+    bool finalized = false;
+    // device layout
+    int n = 0, nPad = 0, nHalo = 0, nBoundary = 0;
+    long long stride = 0;
+    int indexForm = CHIMP_INDEX_TABLE;
+    int32_t *d_table = nullptr, *d_label = nullptr;
+    uint32_t *d_bbmask = nullptr, *d_pmask = nullptr;
+    int32_t *d_base = nullptr, *d_rows = nullptr;
+    int nTiles = 0, nRows = 0;
+    double *d_f[2] = {nullptr, nullptr};
+    int cur = 0;
+    double *d_rho = nullptr, *d_vel = nullptr;
+    bool hasPressure = false;
+    // one-phase attributes
+    bool onePhase = false;
+    double *d_forceOn = nullptr, *d_addSource = nullptr, *d_srcPerLabel = nullptr, *d_massPartial = nullptr;
+    int32_t *d_labelAttr = nullptr;
+    int nLabels = 0;
+    std::vector<double> scalePerLabel;
+    double rhoW = 1.0;
+    // streams
+    cudaStream_t stream = nullptr, haloStream = nullptr;
+    bool ownStream = false;
+    cudaEvent_t evBoundary = nullptr, evHalo = nullptr, evStep = nullptr;
+    chimp_exchange_fn exchange = nullptr;
+    void *exchangeUser = nullptr;
+    long long steps = 0;
+};
+
+namespace {
+
+int check(chimp_lattice *c, bool needFinal)
+{
+    if (!c) return fail("null lattice handle");
+    if (needFinal && !c->finalized) return fail("lattice not finalized (call chimp_finalize first)");
+    if (!needFinal && c->finalized) return fail("lattice already finalized");
+    return 0;
+}
+
+int allocateState(chimp_lattice *c)
+{
+    const size_t planeBytes = (size_t)c->stride * c->li.nQ * c->nFields * sizeof(double);
+    for (int b = 0; b < 2; ++b) {
+        CUDA_OK(cudaMalloc(&c->d_f[b], planeBytes));
+        CUDA_OK(cudaMemsetAsync(c->d_f[b], 0, planeBytes, c->stream));
+    }
+    CUDA_OK(cudaMalloc(&c->d_rho, (size_t)c->nPad * c->nFields * sizeof(double)));
+    CUDA_OK(cudaMalloc(&c->d_vel, (size_t)c->nPad * c->li.nD * sizeof(double)));
+    CUDA_OK(cudaMemsetAsync(c->d_rho, 0, (size_t)c->nPad * c->nFields * sizeof(double), c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_vel, 0, (size_t)c->nPad * c->li.nD * sizeof(double), c->stream));
+    return 0;
+}
+
+int buildRankIndex(chimp_lattice *c)
+{
+    const int nQ = c->li.nQ;
+    c->nTiles = c->nPad / 32;
+    CUDA_OK(cudaMalloc(&c->d_bbmask, (size_t)c->nPad * sizeof(uint32_t)));
+    CUDA_OK(cudaMemsetAsync(c->d_bbmask, 0, (size_t)c->nPad * sizeof(uint32_t), c->stream));
+    CUDA_OK(cudaMalloc(&c->d_base, (size_t)c->nTiles * nQ * sizeof(int32_t)));
+    int *d_cnt = nullptr;
+    CUDA_OK(cudaMalloc(&d_cnt, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
+    const long long threads = (long long)c->nTiles * nQ * 32;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    classifyTilesKernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->n, c->nPad, nQ, c->nTiles, c->d_base, c->d_bbmask, d_cnt);
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+    int cnt = 0;
+    CUDA_OK(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_cnt);
+    c->nRows = cnt;
+    CUDA_OK(cudaMalloc(&c->d_rows, (size_t)std::max(cnt, 1) * 32 * sizeof(int32_t)));
+    if (cnt > 0) {
+        fillRowsKernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->n, c->nPad, nQ, c->nTiles, c->d_base, c->d_rows);
+        ++g_launches;
+        CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int setupStreams(chimp_lattice *c)
+{
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->ownStream = true;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->haloStream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&c->evBoundary, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->evStep, cudaEventDisableTiming));
+    return 0;
+}
+
+template <class L, int COLL, bool ONEPHASE, int IDX>
+void launchSingle(const StepArgs &a, bool mom, cudaStream_t s)
+{
+    const int count = a.end - a.begin;
+    if (count <= 0) return;
+    const int block = 256;
+    const unsigned grid = (unsigned)((count + block - 1) / block);
+    if (mom) collideStreamKernel<L, COLL, ONEPHASE, true, IDX><<<grid, block, 0, s>>>(a);
+    else collideStreamKernel<L, COLL, ONEPHASE, false, IDX><<<grid, block, 0, s>>>(a);
+    ++g_launches;
+}
+
+template <class L>
+void dispatchSingle(const chimp_lattice *c, const StepArgs &a, int coll, bool mom, cudaStream_t s)
+{
+    const bool op = c->onePhase;
+    const bool rk = c->indexForm == CHIMP_INDEX_RANK;
+#define CH_LAUNCH(COLL, OP, IDX) launchSingle<L, COLL, OP, IDX>(a, mom, s)
+    if (coll == CHIMP_BGK) {
+        if (op) { if (rk) CH_LAUNCH(COLL_BGK, true, IDX_RANK); else CH_LAUNCH(COLL_BGK, true, IDX_TABLE); }
+        else    { if (rk) CH_LAUNCH(COLL_BGK, false, IDX_RANK); else CH_LAUNCH(COLL_BGK, false, IDX_TABLE); }
+    } else {
+        if (op) { if (rk) CH_LAUNCH(COLL_TRT, true, IDX_RANK); else CH_LAUNCH(COLL_TRT, true, IDX_TABLE); }
+        else    { if (rk) CH_LAUNCH(COLL_TRT, false, IDX_RANK); else CH_LAUNCH(COLL_TRT, false, IDX_TABLE); }
+    }
+#undef CH_LAUNCH
+}
+
+void dispatchSingleLattice(const chimp_lattice *c, const StepArgs &a, int coll, bool mom, cudaStream_t s)
+{
+    switch (c->lattice) {
+    case CHIMP_D2Q9: dispatchSingle<D2Q9>(c, a, coll, mom, s); break;
+    case CHIMP_D3Q19: dispatchSingle<D3Q19>(c, a, coll, mom, s); break;
+    case CHIMP_D3Q27: dispatchSingle<D3Q27>(c, a, coll, mom, s); break;
+    }
+}
+
+} // namespace
+
+// =========================================================================================
+// C-ABI
+// =========================================================================================
+extern "C" {
+
+const char *chimp_last_error(void) { return g_err.c_str(); }
+int chimp_version(void) { return 100; }
+long long chimp_launch_count(void) { return g_launches.load(); }
+int chimp_lattice_nq(int l) { return latInfo(l).nQ; }
+int chimp_lattice_nd(int l) { return latInfo(l).nD; }
+int chimp_lattice_c(int l, int q, int d)
+{
+    switch (l) {
+    case CHIMP_D2Q9: return D2Q9::c(q, d);
+    case CHIMP_D3Q19: return D3Q19::c(q, d);
+    case CHIMP_D3Q27: return D3Q27::c(q, d);
+    }
+    return 0;
+}
+double chimp_lattice_w(int l, int q)
+{
+    switch (l) {
+    case CHIMP_D2Q9: return D2Q9::w(q);
+    case CHIMP_D3Q19: return D3Q19::w(q);
+    case CHIMP_D3Q27: return D3Q27::w(q);
+    }
+    return 0.0;
+}
+int chimp_lattice_reverse(int l, int q) { return revDir(latInfo(l), q); }
+
+int chimp_create(chimp_lattice **out, int lattice, int n_nodes, const int32_t *neigh, int n_bulk,
+                 const int32_t *bulk, int n_fields, int device)
+{
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    const LatInfo li = latInfo(lattice);
+    if (li.nQ == 0) return fail("unknown lattice id %d", lattice);
+    if (n_fields < 1 || n_fields > 2) return fail("n_fields must be 1 or 2, got %d", n_fields);
+    if (n_nodes < 1 || n_bulk < 0 || !neigh || (!bulk && n_bulk > 0)) return fail("bad table arguments");
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+        return fail("no CUDA device available: this engine has no CPU fallback");
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    CUDA_OK(cudaSetDevice(device));
+    for (int b = 0; b < n_bulk; ++b) {
+        if (bulk[b] <= 0 || bulk[b] >= n_nodes) return fail("bulk[%d]=%d outside (0,%d)", b, bulk[b], n_nodes);
+        if (b && bulk[b] <= bulk[b - 1]) return fail("bulk list must be strictly ascending (LBgeometry.h:11-21)");
+    }
+    for (long long k = 0; k < (long long)n_nodes * li.nQ; ++k)
+        if (neigh[k] < 0 || neigh[k] >= n_nodes) return fail("neighbor entry %lld = %d outside [0,%d)", k, neigh[k], n_nodes);
+    chimp_lattice *c = new chimp_lattice;
+    c->lattice = lattice;
+    c->li = li;
+    c->device = device;
+    c->nFields = n_fields;
+    c->nNodes = n_nodes;
+    c->neigh.assign(neigh, neigh + (size_t)n_nodes * li.nQ);
+    c->bulk.assign(bulk, bulk + n_bulk);
+    if (setupStreams(c)) { delete c; return 1; }
+    *out = c;
+    return 0;
+}
+
+int chimp_add_halfway_bb(chimp_lattice *c, int n_bnd, const int32_t *nodes, const int32_t *n_beta,
+                         const int32_t *n_gamma, const int32_t *n_delta, const int32_t *links)
+{
+    if (check(c, false)) return 1;
+    const int nQ = c->li.nQ, P = c->li.nPairs;
+    for (int b = 0; b < n_bnd; ++b) {
+        const int node = nodes[b];
+        if (node <= 0 || node >= c->nNodes) return fail("bounce-back node %d out of range", node);
+        if (n_beta[b] + n_gamma[b] + n_delta[b] != P) return fail("bounce-back node %d: link counts do not sum to nDirPairs", node);
+        const int32_t *l = links + (size_t)b * P;
+        // LBhalfwaybb.h:52-61
+        for (int k = 0; k < n_beta[b]; ++k) {
+            const int beta = l[k], br = revDir(c->li, beta);
+            c->ops.push_back({0, node, beta, c->neigh[(size_t)node * nQ + br], br});
+        }
+        for (int k = 0; k < n_delta[b]; ++k) {
+            const int d = l[n_beta[b] + n_gamma[b] + k], dr = revDir(c->li, d);
+            c->ops.push_back({0, node, d, c->neigh[(size_t)node * nQ + dr], dr});
+            c->ops.push_back({0, node, dr, c->neigh[(size_t)node * nQ + d], d});
+        }
+    }
+    return 0;
+}
+
+int chimp_add_links(chimp_lattice *c, int kind, int n_links, const int32_t *l4)
+{
+    if (check(c, false)) return 1;
+    if (kind < 0 || kind > 2) return fail("unknown link kind %d", kind);
+    for (int k = 0; k < n_links; ++k) {
+        const int nf = l4[4 * k], qu = l4[4 * k + 1], nw = l4[4 * k + 2], qk = l4[4 * k + 3];
+        if (nf <= 0 || nf >= c->nNodes || nw < 0 || nw >= c->nNodes || qu < 0 || qu >= c->li.nQ || qk < 0 || qk >= c->li.nQ)
+            return fail("link %d out of range", k);
+        c->ops.push_back({kind, nf, qu, nw, qk});
+    }
+    if (kind == CHIMP_LINK_PRESSURE && n_links > 0) c->hasPressure = true;
+    return 0;
+}
+
+int chimp_add_neighbor(chimp_lattice *c, int neig_rank, int n_send, const int32_t *nodes_to_send,
+                       const int32_t *n_dir_send, const int32_t *dir_list_send, int n_recv,
+                       const int32_t *nodes_received, const int32_t *n_dir_recv, const int32_t *dir_list_recv)
+{
+    if (check(c, false)) return 1;
+    if (!c->nbrs.empty() && c->nbrs.back().rank >= neig_rank) return fail("neighbour ranks must be added in ascending order");
+    Neighbor nb;
+    nb.rank = neig_rank;
+    nb.sendNodes.assign(nodes_to_send, nodes_to_send + n_send);
+    nb.nDirSend.assign(n_dir_send, n_dir_send + n_send);
+    long long ns = 0;
+    for (int k = 0; k < n_send; ++k) ns += n_dir_send[k];
+    nb.dirSend.assign(dir_list_send, dir_list_send + ns);
+    nb.recvNodes.assign(nodes_received, nodes_received + n_recv);
+    nb.nDirRecv.assign(n_dir_recv, n_dir_recv + n_recv);
+    long long nr = 0;
+    for (int k = 0; k < n_recv; ++k) nr += n_dir_recv[k];
+    nb.dirRecv.assign(dir_list_recv, dir_list_recv + nr);
+    nb.sendCount = ns;
+    nb.recvCount = nr;
+    c->nbrs.push_back(std::move(nb));
+    return 0;
+}
+
+int chimp_set_solid_boundary(chimp_lattice *c, int n_solid, const int32_t *solid_nodes)
+{
+    if (check(c, false)) return 1;
+    c->solidBnd.assign(solid_nodes, solid_nodes + n_solid);
+    return 0;
+}
+
+int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
+{
+    if (check(c, false)) return 1;
+    if (index_form != CHIMP_INDEX_TABLE && index_form != CHIMP_INDEX_RANK) return fail("unknown index form %d", index_form);
+    CUDA_OK(cudaSetDevice(c->device));
+    const LatInfo li = c->li;
+    const int nQ = li.nQ;
+    const int nBulk = (int)c->bulk.size();
+    const int32_t UNSET = -1;
+    // symbolic slot contents: >= 0: (bulkIndex << 1) | reversed ; -1 unset ; <= -2: halo element -2-h
+    std::vector<int32_t> sym((size_t)c->nNodes * nQ, UNSET);
+    std::vector<int32_t> bulkIndex(c->nNodes, -1);
+    for (int b = 0; b < nBulk; ++b) bulkIndex[c->bulk[b]] = b;
+    if (nBulk >= (1 << 30)) return fail("too many nodes for the 32-bit symbolic builder");
+    // 1. push (LBfield.h:350-357), bulk order => last writer wins
+    for (int b = 0; b < nBulk; ++b) {
+        const size_t row = (size_t)c->bulk[b] * nQ;
+        for (int q = 0; q < nQ; ++q) sym[(size_t)c->neigh[row + q] * nQ + q] = b << 1;
+    }
+    // 2. ghost exchange (LBmonlatmpi.h:236-297)
+    long long haloTotal = 0;
+    std::vector<std::vector<long long>> sendSrc(c->nbrs.size()); // q * nBulk + b (bulk-index space)
+    std::vector<std::vector<int>> haloDirCount(1, std::vector<int>(nQ, 0));
+    std::vector<std::pair<int, int>> haloQH; // halo element -> (q, index within direction q)
+    for (size_t k = 0; k < c->nbrs.size(); ++k) {
+        Neighbor &nb = c->nbrs[k];
+        size_t cnt = 0;
+        for (size_t s = 0; s < nb.sendNodes.size(); ++s)
+            for (int j = 0; j < nb.nDirSend[s]; ++j, ++cnt) {
+                const int q = nb.dirSend[cnt];
+                const int node = nb.sendNodes[s];
+                if (q < 0 || q >= nQ || node < 0 || node >= c->nNodes) return fail("neighbour %d: bad send entry", nb.rank);
+                const int ghost = c->neigh[(size_t)node * nQ + q];
+                const int32_t code = sym[(size_t)ghost * nQ + q];
+                if (code < 0 || (code & 1)) return fail("neighbour %d: send slot (q=%d, ghost node %d) was not pushed by an own node", nb.rank, q, ghost);
+                sendSrc[k].push_back((long long)q * nBulk + (code >> 1));
+            }
+    }
+    for (size_t k = 0; k < c->nbrs.size(); ++k) {
+        Neighbor &nb = c->nbrs[k];
+        size_t cnt = 0;
+        for (size_t s = 0; s < nb.recvNodes.size(); ++s)
+            for (int j = 0; j < nb.nDirRecv[s]; ++j, ++cnt) {
+                const int q = nb.dirRecv[cnt];
+                const int node = nb.recvNodes[s];
+                if (q < 0 || q >= nQ || node < 0 || node >= c->nNodes) return fail("neighbour %d: bad recv entry", nb.rank);
+                const int real = c->neigh[(size_t)node * nQ + q];
+                sym[(size_t)real * nQ + q] = (int32_t)(-2 - haloTotal);
+                haloQH.push_back({q, haloDirCount[0][q]++});
+                ++haloTotal;
+                if (haloTotal > (1ll << 30)) return fail("halo too large");
+            }
+    }
+    // 3. boundary copies in application order
+    std::vector<uint32_t> pmaskB(nBulk, 0);
+    auto orient = [&](int32_t code, int sq, int dq, int32_t &outCode) -> bool {
+        if (code == UNSET) { outCode = UNSET; return true; }
+        if (code <= -2) { outCode = code; return sq == dq; }
+        const int actual = (code & 1) ? revDir(li, sq) : sq;
+        if (actual == dq) outCode = code & ~1;
+        else if (actual == revDir(li, dq)) outCode = code | 1;
+        else return false;
+        return true;
+    };
+    for (const Op &op : c->ops) {
+        const size_t d = (size_t)op.dn * nQ + op.dq, s = (size_t)op.sn * nQ + op.sq;
+        int32_t v;
+        if (op.kind == 0) {
+            if (!orient(sym[s], op.sq, op.dq, v)) return fail("boundary copy (%d,%d)<-(%d,%d): unsupported direction change", op.dn, op.dq, op.sn, op.sq);
+            sym[d] = v;
+        } else if (op.kind == 1) {
+            const int32_t code = sym[s];
+            const int b = bulkIndex[op.dn];
+            if (b < 0 || code != (b << 1) || op.dq != revDir(li, op.sq))
+                return fail("pressure link at node %d: the known population must be the node's own pushed value", op.dn);
+            pmaskB[b] |= 1u << op.sq;
+            sym[d] = code | 1;
+        } else {
+            int32_t a, bcode;
+            if (!orient(sym[s], op.sq, op.dq, a) || !orient(sym[d], op.dq, op.sq, bcode))
+                return fail("fluid-fluid link (%d,%d)<->(%d,%d): unsupported direction change", op.dn, op.dq, op.sn, op.sq);
+            sym[d] = a;
+            sym[s] = bcode;
+        }
+    }
+    // 4. device order: halo-coupled nodes first when requested
+    std::vector<int32_t> devOf(nBulk, -1), order;
+    order.reserve(nBulk);
+    int nBoundary = 0;
+    if (boundary_first && !c->nbrs.empty()) {
+        std::vector<char> coupled(nBulk, 0);
+        for (auto &v : sendSrc)
+            for (long long e : v) coupled[e % nBulk] = 1;
+        for (int b = 0; b < nBulk; ++b) {
+            const size_t row = (size_t)c->bulk[b] * nQ;
+            for (int q = 0; q < nQ && !coupled[b]; ++q)
+                if (sym[row + q] <= -2) coupled[b] = 1;
+        }
+        for (int b = 0; b < nBulk; ++b) if (coupled[b]) order.push_back(b);
+        nBoundary = (int)order.size();
+        for (int b = 0; b < nBulk; ++b) if (!coupled[b]) order.push_back(b);
+    } else {
+        for (int b = 0; b < nBulk; ++b) order.push_back(b);
+    }
+    const int nSlots = (int)order.size();
+    for (int i = 0; i < nSlots; ++i) if (order[i] >= 0) devOf[order[i]] = i;
+    c->n = nSlots;
+    // the first launch covers whole warp tiles: it may include a few uncoupled nodes
+    c->nBoundary = nBoundary ? std::min(((nBoundary + 31) / 32) * 32, nSlots) : 0;
+    c->nPad = ((nSlots + 31) / 32) * 32;
+    int maxHaloDir = 0;
+    for (int q = 0; q < nQ; ++q) maxHaloDir = std::max(maxHaloDir, haloDirCount[0][q]);
+    c->nHalo = ((maxHaloDir + 15) / 16) * 16;
+    c->stride = (long long)c->nPad + c->nHalo;
+    // 5. pull table in device order
+    std::vector<int32_t> table((size_t)nQ * c->nPad, -1), label(c->nPad, 0);
+    std::vector<uint32_t> pmask(c->nPad, 0);
+    std::vector<uint8_t> pulled((size_t)nBulk * nQ, 0);
+    for (int i = 0; i < nSlots; ++i) {
+        const int b = order[i];
+        label[i] = c->bulk[b];
+        pmask[i] = pmaskB[b];
+        const size_t row = (size_t)c->bulk[b] * nQ;
+        for (int q = 0; q < nQ; ++q) {
+            const int32_t code = sym[row + q];
+            int32_t t;
+            if (code == UNSET)
+                return fail("node %d direction %d has no upstream writer: geometry must be closed (walls with bounce back) or periodic", c->bulk[b], q);
+            if (code <= -2) {
+                const auto &qh = haloQH[(size_t)(-2 - code)];
+                t = c->nPad + qh.second;
+            } else {
+                const int sb = code >> 1;
+                const int sq = (code & 1) ? revDir(li, q) : q;
+                if (pulled[(size_t)sb * nQ + sq]++) return fail("population (q=%d, node %d) is pulled twice: open boundary through the shared dummy node 0", sq, c->bulk[sb]);
+                if (code & 1) {
+                    if (sb != b) return fail("node %d direction %d bounces a foreign node's population (unsupported)", c->bulk[b], q);
+                    t = -1;
+                } else t = devOf[sb];
+            }
+            table[(size_t)q * c->nPad + i] = t;
+        }
+    }
+    // 6. upload
+    CUDA_OK(cudaMalloc(&c->d_table, table.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpy(c->d_table, table.data(), table.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_label, label.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpy(c->d_label, label.data(), label.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_pmask, pmask.size() * sizeof(uint32_t)));
+    CUDA_OK(cudaMemcpy(c->d_pmask, pmask.data(), pmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // halo lists (slot offsets inside one field's planes)
+    long long haloOff = 0;
+    for (size_t k = 0; k < c->nbrs.size(); ++k) {
+        Neighbor &nb = c->nbrs[k];
+        std::vector<long long> src(sendSrc[k].size()), dst((size_t)nb.recvCount);
+        for (size_t e = 0; e < src.size(); ++e) {
+            const long long q = sendSrc[k][e] / nBulk, b = sendSrc[k][e] % nBulk;
+            src[e] = q * c->stride + devOf[b];
+        }
+        for (long long e = 0; e < nb.recvCount; ++e) {
+            const auto &qh = haloQH[(size_t)(haloOff + e)];
+            dst[e] = (long long)qh.first * c->stride + c->nPad + qh.second;
+        }
+        haloOff += nb.recvCount;
+        if (!src.empty()) {
+            CUDA_OK(cudaMalloc(&nb.d_sendSrc, src.size() * sizeof(long long)));
+            CUDA_OK(cudaMemcpy(nb.d_sendSrc, src.data(), src.size() * sizeof(long long), cudaMemcpyHostToDevice));
+            CUDA_OK(cudaMalloc(&nb.d_sendBuf, src.size() * c->nFields * sizeof(double)));
+        }
+        if (!dst.empty()) {
+            CUDA_OK(cudaMalloc(&nb.d_recvDst, dst.size() * sizeof(long long)));
+            CUDA_OK(cudaMemcpy(nb.d_recvDst, dst.data(), dst.size() * sizeof(long long), cudaMemcpyHostToDevice));
+            CUDA_OK(cudaMalloc(&nb.d_recvBuf, dst.size() * c->nFields * sizeof(double)));
+        }
+    }
+    c->indexForm = index_form;
+    if (index_form == CHIMP_INDEX_RANK && buildRankIndex(c)) return 1;
+    if (allocateState(c)) return 1;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    // release host inputs
+    std::vector<int32_t>().swap(c->neigh);
+    std::vector<Op>().swap(c->ops);
+    c->finalized = true;
+    return 0;
+}
+
+int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk, int n_pad, int n_halo,
+                                   const int32_t *table_dev, const int32_t *label_dev, int n_fields,
+                                   int index_form, int device)
+{
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    const LatInfo li = latInfo(lattice);
+    if (li.nQ == 0) return fail("unknown lattice id %d", lattice);
+    if (n_fields < 1 || n_fields > 2) return fail("n_fields must be 1 or 2");
+    if (n_pad % 32 || n_pad < n_bulk || n_halo % 16) return fail("n_pad must be a multiple of 32 >= n_bulk, n_halo a multiple of 16");
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+        return fail("no CUDA device available: this engine has no CPU fallback");
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    CUDA_OK(cudaSetDevice(device));
+    chimp_lattice *c = new chimp_lattice;
+    c->lattice = lattice;
+    c->li = li;
+    c->device = device;
+    c->nFields = n_fields;
+    if (setupStreams(c)) { delete c; return 1; }
+    c->n = n_bulk;
+    c->nPad = n_pad;
+    c->nHalo = n_halo;
+    c->stride = (long long)n_pad + n_halo;
+    const size_t tb = (size_t)li.nQ * n_pad * sizeof(int32_t);
+    CUDA_OK(cudaMalloc(&c->d_table, tb));
+    CUDA_OK(cudaMemcpyAsync(c->d_table, table_dev, tb, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(cudaMalloc(&c->d_label, (size_t)n_pad * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpyAsync(c->d_label, label_dev, (size_t)n_pad * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    c->indexForm = index_form;
+    if (index_form == CHIMP_INDEX_RANK && buildRankIndex(c)) { chimp_destroy(c); return 1; }
+    if (allocateState(c)) { chimp_destroy(c); return 1; }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->finalized = true;
+    *out = c;
+    return 0;
+}
+
+void chimp_destroy(chimp_lattice *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    freeDev(c->d_table); freeDev(c->d_label); freeDev(c->d_bbmask); freeDev(c->d_pmask);
+    freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
+    freeDev(c->d_rho); freeDev(c->d_vel);
+    freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
+    freeDev(c->d_labelAttr);
+    for (auto &nb : c->nbrs) { freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf); }
+    if (c->evBoundary) cudaEventDestroy(c->evBoundary);
+    if (c->evHalo) cudaEventDestroy(c->evHalo);
+    if (c->evStep) cudaEventDestroy(c->evStep);
+    if (c->haloStream) cudaStreamDestroy(c->haloStream);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---- state transfer ---------------------------------------------------------------------
+static int maxLabelRows(chimp_lattice *c, long long &rows)
+{
+    // the host arrays have grid.size() rows; without the host tables (device-table path) the
+    // largest label + 1 is the row count the caller must provide
+    rows = c->nNodes;
+    return 0;
+}
+
+int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
+{
+    if (check(c, true)) return 1;
+    if (c->nNodes <= 0) return fail("upload in reference layout needs a lattice created from reference tables");
+    CUDA_OK(cudaSetDevice(c->device));
+    long long rows;
+    maxLabelRows(c, rows);
+    const size_t bytes = (size_t)rows * c->nFields * c->li.nQ * sizeof(double);
+    double *d_aos = nullptr;
+    CUDA_OK(cudaMalloc(&d_aos, bytes));
+    CUDA_OK(cudaMemcpyAsync(d_aos, f_aos, bytes, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)((c->n + 255) / 256);
+    double *X = c->d_f[c->cur];
+    switch (c->lattice) {
+    case CHIMP_D2Q9: scatterStateKernel<D2Q9><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q19: scatterStateKernel<D3Q19><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q27: scatterStateKernel<D3Q27><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    }
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_aos);
+    return 0;
+}
+
+int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
+{
+    if (check(c, true)) return 1;
+    if (c->nNodes <= 0) return fail("download in reference layout needs a lattice created from reference tables");
+    CUDA_OK(cudaSetDevice(c->device));
+    long long rows;
+    maxLabelRows(c, rows);
+    const size_t bytes = (size_t)rows * c->nFields * c->li.nQ * sizeof(double);
+    double *d_aos = nullptr;
+    CUDA_OK(cudaMalloc(&d_aos, bytes));
+    // rows that are not own bulk nodes keep the caller's content
+    CUDA_OK(cudaMemcpyAsync(d_aos, f_aos, bytes, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)((c->n + 255) / 256);
+    const double *X = c->d_f[c->cur];
+    switch (c->lattice) {
+    case CHIMP_D2Q9: gatherStateKernel<D2Q9><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q19: gatherStateKernel<D3Q19><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q27: gatherStateKernel<D3Q27><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    }
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(f_aos, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_aos);
+    return 0;
+}
+
+static int downloadPlanes(chimp_lattice *c, double *host, const double *planes, int nComp, int aosStride, int aosOffset)
+{
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->nNodes * aosStride * sizeof(double);
+    double *d_aos = nullptr;
+    CUDA_OK(cudaMalloc(&d_aos, bytes));
+    CUDA_OK(cudaMemcpyAsync(d_aos, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)((c->n + 255) / 256);
+    planesToAosKernel<<<grid, 256, 0, c->stream>>>(d_aos, planes, c->d_label, c->n, c->nPad, nComp, aosStride, aosOffset);
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(host, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_aos);
+    return 0;
+}
+
+int chimp_download_rho(chimp_lattice *c, double *rho_sca, int n_fields_host)
+{
+    if (check(c, true)) return 1;
+    if (c->nNodes <= 0) return fail("needs a lattice created from reference tables");
+    if (n_fields_host < c->nFields) return fail("host ScalarField has fewer fields than the lattice");
+    for (int f = 0; f < c->nFields; ++f)
+        if (downloadPlanes(c, rho_sca, c->d_rho + (size_t)f * c->nPad, 1, n_fields_host, f)) return 1;
+    return 0;
+}
+
+int chimp_download_vel(chimp_lattice *c, double *vel_vec)
+{
+    if (check(c, true)) return 1;
+    if (c->nNodes <= 0) return fail("needs a lattice created from reference tables");
+    return downloadPlanes(c, vel_vec, c->d_vel, c->li.nD, c->li.nD, 0);
+}
+
+int chimp_set_one_phase_attributes(chimp_lattice *c, const double *force_on, const int32_t *interior_label,
+                                   const double *add_mass_source, int n_labels, const double *scale_per_label,
+                                   double rho_w)
+{
+    if (check(c, true)) return 1;
+    if (c->nNodes <= 0) return fail("needs a lattice created from reference tables");
+    if (n_labels < 1) return fail("n_labels must be >= 1");
+    CUDA_OK(cudaSetDevice(c->device));
+    std::vector<int32_t> label(c->nPad);
+    CUDA_OK(cudaMemcpy(label.data(), c->d_label, (size_t)c->nPad * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<double> on(c->nPad, 0.0), add(c->nPad, 0.0);
+    std::vector<int32_t> lab(c->nPad, 0);
+    for (int i = 0; i < c->n; ++i) {
+        const int l = label[i];
+        if (l <= 0) continue;
+        on[i] = force_on[l];
+        add[i] = add_mass_source[l];
+        lab[i] = interior_label[l];
+        if (lab[i] < 0 || lab[i] >= n_labels) return fail("interior label %d of node %d outside [0,%d)", lab[i], l, n_labels);
+    }
+    freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_labelAttr); freeDev(c->d_srcPerLabel);
+    CUDA_OK(cudaMalloc(&c->d_forceOn, on.size() * sizeof(double)));
+    CUDA_OK(cudaMemcpy(c->d_forceOn, on.data(), on.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_addSource, add.size() * sizeof(double)));
+    CUDA_OK(cudaMemcpy(c->d_addSource, add.data(), add.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_labelAttr, lab.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpy(c->d_labelAttr, lab.data(), lab.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_srcPerLabel, (size_t)n_labels * sizeof(double)));
+    CUDA_OK(cudaMemset(c->d_srcPerLabel, 0, (size_t)n_labels * sizeof(double)));
+    c->nLabels = n_labels;
+    c->scalePerLabel.assign(scale_per_label, scale_per_label + n_labels);
+    c->rhoW = rho_w;
+    c->onePhase = true;
+    return 0;
+}
+
+// ---- stepping -----------------------------------------------------------------------------
+int chimp_step_single(chimp_lattice *c, const chimp_single_params *p, int n_steps)
+{
+    if (check(c, true)) return 1;
+    if (!p) return fail("params is null");
+    if (c->nFields != 1) return fail("chimp_step_single needs a one-field lattice");
+    if (p->collision != CHIMP_BGK && p->collision != CHIMP_TRT) return fail("unknown collision %d", p->collision);
+    if (c->hasPressure && !c->onePhase) return fail("pressure links need chimp_set_one_phase_attributes");
+    CUDA_OK(cudaSetDevice(c->device));
+    StepArgs a{};
+    a.stride = c->stride;
+    a.n = c->n;
+    a.nPad = c->nPad;
+    a.idx.table = c->d_table;
+    a.idx.bbmask = c->d_bbmask;
+    a.idx.base = c->d_base;
+    a.idx.rows = c->d_rows;
+    a.idx.nTiles = c->nTiles;
+    // LBcollision.h:39,65-66,91,113-114,206,228-229: per-call constants of the reference helpers
+    a.tauInv = 1.0 / p->tau;
+    a.tauFactor = (1 - 0.5 / p->tau);
+    if (p->collision == CHIMP_TRT) {
+        a.tauSymInv = 1.0 / p->tau_sym;
+        a.tauAntiInv = 1.0 / p->tau_anti;
+        a.symFactor = (1 - 0.5 / p->tau_sym);
+        a.antiFactor = (1 - 0.5 / p->tau_anti);
+    }
+    for (int d = 0; d < 3; ++d) a.F[d] = d < c->li.nD ? p->force[d] : 0.0;
+    a.forceOn = c->d_forceOn;
+    a.addSource = c->d_addSource;
+    a.label = c->d_labelAttr;
+    a.srcPerLabel = c->d_srcPerLabel;
+    a.pmask = c->hasPressure ? c->d_pmask : nullptr;
+    a.rhoW = c->rhoW;
+    a.rho = c->d_rho;
+    a.vel = c->d_vel;
+    const bool multi = !c->nbrs.empty();
+    for (int s = 0; s < n_steps; ++s) {
+        const bool mom = (s == n_steps - 1);
+        a.fin = c->d_f[c->cur];
+        a.fout = c->d_f[c->cur ^ 1];
+        if (c->onePhase && c->nLabels > 1) return fail("mass-conservation source with interior domains is not implemented yet");
+        if (!multi) {
+            a.begin = 0;
+            a.end = c->n;
+            dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+        } else {
+            // halo-coupled nodes first; their packed populations travel while the interior runs
+            a.begin = 0;
+            a.end = c->nBoundary ? std::min(c->nBoundary, c->n) : c->n;
+            dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+            for (auto &nb : c->nbrs)
+                if (nb.sendCount) {
+                    haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.d_sendBuf, a.fout, nb.d_sendSrc, (int)nb.sendCount);
+                    ++g_launches;
+                }
+            CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
+            CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+            if (c->exchange && c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
+            for (auto &nb : c->nbrs)
+                if (nb.recvCount) {
+                    haloUnpackKernel<<<(unsigned)((nb.recvCount + 255) / 256), 256, 0, c->haloStream>>>(a.fout, nb.d_recvBuf, nb.d_recvDst, (int)nb.recvCount);
+                    ++g_launches;
+                }
+            CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
+            if (c->nBoundary && c->nBoundary < c->n) {
+                a.begin = c->nBoundary;
+                a.end = c->n;
+                dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+            }
+            CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
+        }
+        c->cur ^= 1;
+        ++c->steps;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int chimp_set_twophase_density(chimp_lattice *, const double *) { return fail("twophase path not built yet"); }
+int chimp_step_twophase(chimp_lattice *, const chimp_twophase_params *, int) { return fail("twophase path not built yet"); }
+int chimp_download_phase_field(chimp_lattice *, double *) { return fail("twophase path not built yet"); }
+double chimp_last_flux_force(chimp_lattice *) { return 0.0; }
+
+// ---- halo plumbing ----------------------------------------------------------------------
+int chimp_num_neighbors(chimp_lattice *c) { return c ? (int)c->nbrs.size() : 0; }
+int chimp_neighbor_info(chimp_lattice *c, int k, int *neig_rank, long long *send_count, long long *recv_count)
+{
+    if (!c || k < 0 || k >= (int)c->nbrs.size()) return fail("bad neighbour index");
+    if (neig_rank) *neig_rank = c->nbrs[k].rank;
+    if (send_count) *send_count = c->nbrs[k].sendCount * c->nFields;
+    if (recv_count) *recv_count = c->nbrs[k].recvCount * c->nFields;
+    return 0;
+}
+void *chimp_send_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].d_sendBuf : nullptr; }
+void *chimp_recv_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].d_recvBuf : nullptr; }
+int chimp_set_exchange_callback(chimp_lattice *c, chimp_exchange_fn fn, void *user)
+{
+    if (!c) return fail("null lattice handle");
+    c->exchange = fn;
+    c->exchangeUser = user;
+    return 0;
+}
+int chimp_set_stream(chimp_lattice *c, void *s)
+{
+    if (!c) return fail("null lattice handle");
+    if (c->ownStream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)s;
+    c->ownStream = false;
+    return 0;
+}
+int chimp_synchronize(chimp_lattice *c)
+{
+    if (!c) return fail("null lattice handle");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->haloStream));
+    return 0;
+}
+
+// ---- introspection ------------------------------------------------------------------------
+int chimp_num_own_nodes(chimp_lattice *c) { return c ? c->n : 0; }
+int chimp_download_pull_table(chimp_lattice *c, int32_t *table, int32_t *labels)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    for (int q = 0; q < c->li.nQ; ++q)
+        CUDA_OK(cudaMemcpy(table + (size_t)q * c->n, c->d_table + (size_t)q * c->nPad, (size_t)c->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(labels, c->d_label, (size_t)c->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+double chimp_irregular_fraction(chimp_lattice *c)
+{
+    if (!c || c->indexForm != CHIMP_INDEX_RANK || c->nTiles == 0) return 0.0;
+    return (double)c->nRows / ((double)c->nTiles * c->li.nQ);
+}
+double chimp_index_bytes_per_node(chimp_lattice *c)
+{
+    if (!c || c->n == 0) return 0.0;
+    if (c->indexForm == CHIMP_INDEX_TABLE) return 4.0 * c->li.nQ;
+    return (4.0 * c->nPad + 4.0 * c->nTiles * c->li.nQ + 128.0 * c->nRows) / c->n;
+}
+long long chimp_plane_stride(chimp_lattice *c) { return c ? c->stride : 0; }
+
+} // extern "C"

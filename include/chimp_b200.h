@@ -1,0 +1,151 @@
+/* chimp_b200.h -- C-ABI of the B200 lattice-Boltzmann engine.
+ *
+ * The reference (eje74/BADChIMP-cpp) has no FFI: its "API" is the header set pulled in by
+ * src/LBSOLVER.h, consumed by hand-written mains.  Each entry point below names the
+ * reference interface it stands in for.  All pointers are plain host pointers unless a
+ * name says `_dev`; arrays are borrowed for the duration of the call only; every function
+ * returns 0 on success and non-zero on error (message via chimp_last_error()).  The
+ * reference convention (print + exit(1), e.g. LBvtk.h:230-233) is left to the host wrapper.
+ *
+ * One chimp_lattice per (rank, GPU).  Not thread-safe.  Step calls are asynchronous on the
+ * context's stream; download / moment / reduction calls synchronise.
+ */
+#ifndef CHIMP_B200_H
+#define CHIMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct chimp_lattice chimp_lattice;
+
+/* lattice ids: D2Q9 (LBd2q9.h:12), D3Q19 (LBd3q19.h:12), D3Q27 (new, same contract) */
+enum { CHIMP_D2Q9 = 0, CHIMP_D3Q19 = 1, CHIMP_D3Q27 = 2 };
+/* collision operators: calcOmegaBGK (LBcollision.h:27), calcOmegaBGKTRT (LBcollision.h:50) */
+enum { CHIMP_BGK = 0, CHIMP_TRT = 1 };
+/* index forms of the streaming step */
+enum { CHIMP_INDEX_TABLE = 0, CHIMP_INDEX_RANK = 1 };
+/* link boundary kinds of std_one_phase/main.cpp:138-203 */
+enum { CHIMP_LINK_SOLID = 0, CHIMP_LINK_PRESSURE = 1, CHIMP_LINK_FLUID_SWAP = 2 };
+
+const char *chimp_last_error(void);
+int chimp_version(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+long long chimp_launch_count(void);
+/* lattice constants, as the reference structs expose them (LBd3q19.h:14-42) */
+int chimp_lattice_nq(int lattice);
+int chimp_lattice_nd(int lattice);
+int chimp_lattice_c(int lattice, int q, int d);
+double chimp_lattice_w(int lattice, int q);
+int chimp_lattice_reverse(int lattice, int q);
+
+/* ---- construction: mirrors Grid<L>(vtk) + findBulkNodes (LBgrid.h:127-148, LBgeometry.h:11-21).
+ * neigh is Grid::neigList_ in reference layout [n_nodes * nQ] (LBgrid.h:187-198), bulk is the
+ * ascending list of own fluid labels, n_fields is LbField's nFields (1, or 2 for twophase).
+ * device < 0 uses the current CUDA device. */
+int chimp_create(chimp_lattice **out, int lattice, int n_nodes, const int32_t *neigh, int n_bulk,
+                 const int32_t *bulk, int n_fields, int device);
+
+/* HalfWayBounceBack<L>(bndNodes, nodes, grid) + apply (LBhalfwaybb.h:25-63): per boundary node
+ * the beta (unknown) directions followed by gamma and delta pair directions, nDirPairs entries
+ * per node as in BoundaryHalwWayHelper::linkList_ (LBhalfwayhelperclass.h:163-212). */
+int chimp_add_halfway_bb(chimp_lattice *, int n_bnd, const int32_t *nodes, const int32_t *n_beta,
+                         const int32_t *n_gamma, const int32_t *n_delta, const int32_t *links);
+
+/* link lists {nodeFluid, qUnknown, nodeWall, qKnown} of std_one_phase/main.cpp:27-126, applied
+ * after streaming in the order added (main.cpp:591-597). */
+int chimp_add_links(chimp_lattice *, int kind, int n_links, const int32_t *links4);
+
+/* one MonLatMpi (LBmonlatmpi.h:72-98): ghost exchange lists towards one neighbour rank, in
+ * the reference's list order.  Neighbours must be added in ascending rank order (LBvtk.h:534-544). */
+int chimp_add_neighbor(chimp_lattice *, int neig_rank, int n_send, const int32_t *nodes_to_send,
+                       const int32_t *n_dir_send, const int32_t *dir_list_send, int n_recv,
+                       const int32_t *nodes_received, const int32_t *n_dir_recv, const int32_t *dir_list_recv);
+
+/* scalar-field support rows for twophase: solid boundary nodes (findSolidBndNodes,
+ * LBgeometry.h:37-45) carry a constant colour value derived from the wettability densities. */
+int chimp_set_solid_boundary(chimp_lattice *, int n_solid, const int32_t *solid_nodes);
+
+/* builds the device tables; index_form is CHIMP_INDEX_TABLE or CHIMP_INDEX_RANK.
+ * boundary_first != 0 orders halo-coupled nodes first so that their step can overlap. */
+int chimp_finalize(chimp_lattice *, int index_form, int boundary_first);
+
+/* alternative construction from device-resident pull tables (structured geometry ingest,
+ * replaces vtklb.py -> ASCII -> LBvtk for large cases): table_dev is int32 [nQ][n_pad]
+ * (source slot, -1 = reversed own slot), label_dev int32 [n_pad] reference labels. */
+int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk, int n_pad, int n_halo,
+                                   const int32_t *table_dev, const int32_t *label_dev, int n_fields,
+                                   int index_form, int device);
+
+void chimp_destroy(chimp_lattice *);
+
+/* ---- state transfer in reference layout and labels.
+ * f_aos is LbField::data_ (LBfield.h:300): [(n_fields*nQ)*node + nQ*field + q], n_nodes rows;
+ * only own bulk rows are read / written. */
+int chimp_upload_lbfield(chimp_lattice *, const double *f_aos);
+int chimp_download_lbfield(chimp_lattice *, double *f_aos);
+/* ScalarField rho (LBfield.h:94: [nFields*node + field]) and VectorField vel (LBfield.h:190) as
+ * stored by the last step that was run with moments enabled. */
+int chimp_download_rho(chimp_lattice *, double *rho_sca, int n_fields_host);
+int chimp_download_vel(chimp_lattice *, double *vel_vec);
+
+/* ---- per-node attributes of std_one_phase (main.cpp:253-330), indexed by reference label */
+int chimp_set_one_phase_attributes(chimp_lattice *, const double *force_on, const int32_t *interior_label,
+                                   const double *add_mass_source, int n_labels, const double *scale_per_label,
+                                   double rho_w);
+
+/* ---- stepping.  n_steps full iterations (collide, stream, exchange, boundary); rho / vel
+ * are stored on the last step only (they are the moments the reference holds after the same
+ * number of iterations).
+ * chimp_step_single: std_case/main.cpp:109-146 (BGK or TRT + Guo force + bounce back);
+ * with one-phase attributes set it runs std_one_phase/main.cpp:513-597. */
+typedef struct {
+    int collision;          /* CHIMP_BGK / CHIMP_TRT */
+    double tau;             /* BGK */
+    double tau_sym, tau_anti; /* TRT */
+    double force[3];        /* bodyForce(0,0) */
+} chimp_single_params;
+int chimp_step_single(chimp_lattice *, const chimp_single_params *, int n_steps);
+
+/* twophase/main_TWOPHASE.cpp:236-392 (colour gradient, 2 fields, flux-controlled force) */
+typedef struct {
+    double tau0, tau1, sigma, beta, momx;
+    double force[3];        /* y,z components; x is overwritten by the flux controller */
+    long long n_fluid_global; /* numNodesGlobal (main_TWOPHASE.cpp:196-198) */
+} chimp_twophase_params;
+int chimp_set_twophase_density(chimp_lattice *, const double *rho_sca2); /* ScalarField rho(2,size) incl. wall rows */
+int chimp_step_twophase(chimp_lattice *, const chimp_twophase_params *, int n_steps);
+int chimp_download_phase_field(chimp_lattice *, double *cg_sca);
+double chimp_last_flux_force(chimp_lattice *);
+
+/* ---- halo plumbing for N ranks (replaces MonLatMpi::communicateLbField, LBmonlatmpi.h:236-297).
+ * The engine packs outgoing populations into per-neighbour device buffers and unpacks
+ * incoming ones; the transport (NCCL send/recv or peer stores) is supplied by the host. */
+int chimp_num_neighbors(chimp_lattice *);
+int chimp_neighbor_info(chimp_lattice *, int k, int *neig_rank, long long *send_count, long long *recv_count);
+/* device pointers of the packed send / recv buffers of neighbour k (doubles, per field contiguous) */
+void *chimp_send_buffer_dev(chimp_lattice *, int k);
+void *chimp_recv_buffer_dev(chimp_lattice *, int k);
+typedef int (*chimp_exchange_fn)(void *user, void *stream);
+/* called once per step after the boundary nodes were packed, on the halo stream */
+int chimp_set_exchange_callback(chimp_lattice *, chimp_exchange_fn fn, void *user);
+/* use an externally owned stream (e.g. torch's current stream) for all launches */
+int chimp_set_stream(chimp_lattice *, void *cuda_stream);
+int chimp_synchronize(chimp_lattice *);
+
+/* ---- introspection for tests / bench */
+int chimp_num_own_nodes(chimp_lattice *);
+int chimp_download_pull_table(chimp_lattice *, int32_t *table /* [nQ][n_own] */, int32_t *labels /* [n_own] */);
+/* fraction of (tile, q) pairs that needed explicit rows in CHIMP_INDEX_RANK form */
+double chimp_irregular_fraction(chimp_lattice *);
+/* device bytes of index data read per node per step, and of population data */
+double chimp_index_bytes_per_node(chimp_lattice *);
+/* device pointer / geometry of the population planes (for bench timing of the bare kernel) */
+long long chimp_plane_stride(chimp_lattice *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIMP_B200_H */
