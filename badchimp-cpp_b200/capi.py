@@ -1,0 +1,346 @@
+"""ctypes binding of the C-ABI (include/chimp_b200.h -> libchimp_b200.so).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible
+when a lattice is created, the call raises.  Host arrays are numpy arrays in the reference's
+layouts (LbField AoS [(nFields*nQ)*node + nQ*field + q], reference node labels).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import geometry as G
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchimp_b200.so")
+_lib = None
+
+BGK, TRT = 0, 1
+INDEX_TABLE, INDEX_RANK = 0, 1
+LINK_SOLID, LINK_PRESSURE, LINK_FLUID_SWAP = 0, 1, 2
+
+
+class ChimpError(RuntimeError):
+    pass
+
+
+class SingleParams(C.Structure):
+    _fields_ = [("collision", C.c_int), ("tau", C.c_double), ("tau_sym", C.c_double), ("tau_anti", C.c_double),
+                ("force", C.c_double * 3)]
+
+
+class TwoPhaseParams(C.Structure):
+    _fields_ = [("tau0", C.c_double), ("tau1", C.c_double), ("sigma", C.c_double), ("beta", C.c_double),
+                ("momx", C.c_double), ("force", C.c_double * 3), ("n_fluid_global", C.c_longlong)]
+
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
+# every symbol include/chimp_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "chimp_last_error", "chimp_version", "chimp_launch_count", "chimp_lattice_nq", "chimp_lattice_nd",
+    "chimp_lattice_c", "chimp_lattice_w", "chimp_lattice_reverse", "chimp_create", "chimp_add_halfway_bb",
+    "chimp_add_links", "chimp_add_neighbor", "chimp_set_solid_boundary", "chimp_build_host", "chimp_finalize",
+    "chimp_create_from_device_table", "chimp_destroy", "chimp_upload_lbfield", "chimp_download_lbfield",
+    "chimp_download_rho", "chimp_download_vel", "chimp_set_one_phase_attributes", "chimp_step_single",
+    "chimp_set_twophase_density", "chimp_step_twophase", "chimp_download_phase_field", "chimp_last_flux_force",
+    "chimp_num_neighbors", "chimp_neighbor_info", "chimp_send_buffer_dev", "chimp_recv_buffer_dev",
+    "chimp_set_exchange_callback", "chimp_set_stream", "chimp_synchronize", "chimp_num_own_nodes",
+    "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_irregular_fraction",
+    "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
+    "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
+    "chimp_set_halo_buffers", "chimp_halo_stream",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ChimpError("%s is missing: build it with __graft_entry__.build() (nvcc, sm_100a); "
+                             "there is no CPU fallback" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.chimp_last_error.restype = C.c_char_p
+        l.chimp_launch_count.restype = C.c_longlong
+        l.chimp_lattice_w.restype = C.c_double
+        l.chimp_last_flux_force.restype = C.c_double
+        l.chimp_last_flux_force.argtypes = [C.c_void_p]
+        l.chimp_irregular_fraction.restype = C.c_double
+        l.chimp_irregular_fraction.argtypes = [C.c_void_p]
+        l.chimp_index_bytes_per_node.restype = C.c_double
+        l.chimp_index_bytes_per_node.argtypes = [C.c_void_p]
+        l.chimp_plane_stride.restype = C.c_longlong
+        l.chimp_plane_stride.argtypes = [C.c_void_p]
+        l.chimp_send_buffer_dev.restype = C.c_void_p
+        l.chimp_send_buffer_dev.argtypes = [C.c_void_p, C.c_int]
+        l.chimp_recv_buffer_dev.restype = C.c_void_p
+        l.chimp_recv_buffer_dev.argtypes = [C.c_void_p, C.c_int]
+        l.chimp_halo_stream.restype = C.c_void_p
+        l.chimp_halo_stream.argtypes = [C.c_void_p]
+        l.chimp_set_halo_buffers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        l.chimp_destroy.restype = None
+        l.chimp_destroy.argtypes = [C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise ChimpError(lib().chimp_last_error().decode())
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Lattice:
+    """One rank's engine context (chimp_lattice)."""
+
+    def __init__(self, lattice: str, neigh, bulk, n_fields=1, device=-1):
+        self.lattice = lattice
+        self.nq = len(G.BASIS[lattice])
+        self.nd = G.BASIS[lattice].shape[1]
+        neigh = _i32(neigh)
+        bulk = _i32(bulk)
+        self.n_nodes = neigh.shape[0]
+        self.n_fields = n_fields
+        self.h = C.c_void_p()
+        _check(lib().chimp_create(C.byref(self.h), G.LATTICE_ID[lattice], C.c_int(self.n_nodes), _p(neigh),
+                                  C.c_int(len(bulk)), _p(bulk), C.c_int(n_fields), C.c_int(device)))
+        self._cb = None
+
+    @classmethod
+    def from_rank_tables(cls, tab: G.RankTables, n_fields=1, device=-1):
+        return cls(tab.g.lattice, tab.neigh, tab.bulk_nodes(), n_fields, device)
+
+    def close(self):
+        if self.h:
+            lib().chimp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- boundary objects ---------------------------------------------------------------
+    def add_halfway_bb(self, nodes, n_beta, n_gamma, n_delta, links):
+        nodes, n_beta, n_gamma, n_delta, links = map(_i32, (nodes, n_beta, n_gamma, n_delta, links))
+        _check(lib().chimp_add_halfway_bb(self.h, C.c_int(len(nodes)), _p(nodes), _p(n_beta), _p(n_gamma), _p(n_delta),
+                                          _p(links)))
+
+    def add_links(self, kind, links4):
+        links4 = _i32(links4).reshape(-1, 4)
+        _check(lib().chimp_add_links(self.h, C.c_int(kind), C.c_int(len(links4)), _p(links4)))
+
+    def add_neighbor(self, rank, send_nodes, send_ndir, send_dirs, recv_nodes, recv_ndir, recv_dirs):
+        a = [_i32(x) for x in (send_nodes, send_ndir, send_dirs, recv_nodes, recv_ndir, recv_dirs)]
+        _check(lib().chimp_add_neighbor(self.h, C.c_int(rank), C.c_int(len(a[0])), _p(a[0]), _p(a[1]), _p(a[2]),
+                                        C.c_int(len(a[3])), _p(a[3]), _p(a[4]), _p(a[5])))
+
+    def set_solid_boundary(self, nodes):
+        nodes = _i32(nodes)
+        _check(lib().chimp_set_solid_boundary(self.h, C.c_int(len(nodes)), _p(nodes)))
+
+    def build_host(self, boundary_first=False):
+        """runs only the host-side table builder (no CUDA); used by the CPU tests"""
+        _check(lib().chimp_build_host(self.h, C.c_int(1 if boundary_first else 0)))
+
+    def finalize(self, index_form=INDEX_RANK, boundary_first=False):
+        _check(lib().chimp_finalize(self.h, C.c_int(index_form), C.c_int(1 if boundary_first else 0)))
+
+    def host_table(self):
+        """(table [nQ, n], labels [n], pmask [n], info dict) of the host builder"""
+        info = (C.c_longlong * 6)()
+        _check(lib().chimp_host_table_info(self.h, info))
+        n, n_pad, n_halo, stride, n_boundary, _ = [int(x) for x in info]
+        table = np.zeros((self.nq, n), dtype=np.int32)
+        labels = np.zeros(n, dtype=np.int32)
+        pmask = np.zeros(n, dtype=np.uint32)
+        _check(lib().chimp_host_table(self.h, _p(table), _p(labels), _p(pmask)))
+        return table, labels, pmask, dict(n=n, n_pad=n_pad, n_halo=n_halo, stride=stride, n_boundary=n_boundary)
+
+    def host_halo_lists(self, k):
+        """(send_src, recv_dst) slot offsets (q*stride + slot) of neighbour k"""
+        rank = C.c_int()
+        ns, nr = C.c_longlong(), C.c_longlong()
+        _check(lib().chimp_neighbor_info(self.h, C.c_int(k), C.byref(rank), C.byref(ns), C.byref(nr)))
+        ns_f, nr_f = ns.value // self.n_fields, nr.value // self.n_fields
+        src = np.zeros(ns_f, dtype=np.int64)
+        dst = np.zeros(nr_f, dtype=np.int64)
+        _check(lib().chimp_host_halo_lists(self.h, C.c_int(k), _p(src), _p(dst)))
+        return rank.value, src, dst
+
+    # ---- state --------------------------------------------------------------------------
+    def upload(self, f_aos):
+        f_aos = _f64(f_aos)
+        assert f_aos.size == self.n_nodes * self.n_fields * self.nq
+        _check(lib().chimp_upload_lbfield(self.h, _p(f_aos)))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.zeros((self.n_nodes, self.n_fields, self.nq))
+        assert out.flags["C_CONTIGUOUS"] and out.size == self.n_nodes * self.n_fields * self.nq
+        _check(lib().chimp_download_lbfield(self.h, _p(out)))
+        return out
+
+    def download_rho(self, out=None):
+        if out is None:
+            out = np.zeros((self.n_nodes, self.n_fields))
+        _check(lib().chimp_download_rho(self.h, _p(out), C.c_int(out.shape[1])))
+        return out
+
+    def download_vel(self, out=None):
+        if out is None:
+            out = np.zeros((self.n_nodes, self.nd))
+        _check(lib().chimp_download_vel(self.h, _p(out)))
+        return out
+
+    def download_phase_field(self, out=None):
+        if out is None:
+            out = np.zeros(self.n_nodes)
+        _check(lib().chimp_download_phase_field(self.h, _p(out)))
+        return out
+
+    def set_one_phase_attributes(self, force_on, interior, add_source, scale, rho_w=1.0):
+        force_on, add_source, scale = _f64(force_on), _f64(add_source), _f64(scale)
+        interior = _i32(interior)
+        _check(lib().chimp_set_one_phase_attributes(self.h, _p(force_on), _p(interior), _p(add_source),
+                                                    C.c_int(len(scale)), _p(scale), C.c_double(rho_w)))
+
+    def set_twophase_density(self, rho2):
+        rho2 = _f64(rho2)
+        assert rho2.size == self.n_nodes * 2
+        _check(lib().chimp_set_twophase_density(self.h, _p(rho2)))
+
+    # ---- stepping -------------------------------------------------------------------------
+    def step_single(self, n_steps, tau=0.8, force=(0.0, 0.0, 0.0), trt=None):
+        p = SingleParams()
+        p.collision = TRT if trt else BGK
+        p.tau = tau
+        p.tau_sym, p.tau_anti = trt if trt else (0.0, 0.0)
+        F = list(force) + [0.0] * (3 - len(force))
+        p.force[0], p.force[1], p.force[2] = F[0], F[1], F[2]
+        _check(lib().chimp_step_single(self.h, C.byref(p), C.c_int(n_steps)))
+
+    def step_twophase(self, n_steps, tau0, tau1, sigma, beta, momx, force, n_fluid_global):
+        p = TwoPhaseParams()
+        p.tau0, p.tau1, p.sigma, p.beta, p.momx = tau0, tau1, sigma, beta, momx
+        F = list(force) + [0.0] * (3 - len(force))
+        p.force[0], p.force[1], p.force[2] = F[0], F[1], F[2]
+        p.n_fluid_global = int(n_fluid_global)
+        _check(lib().chimp_step_twophase(self.h, C.byref(p), C.c_int(n_steps)))
+
+    def _single_params(self, tau, force, trt):
+        p = SingleParams()
+        p.collision = TRT if trt else BGK
+        p.tau = tau
+        p.tau_sym, p.tau_anti = trt if trt else (0.0, 0.0)
+        F = list(force) + [0.0] * (3 - len(force))
+        p.force[0], p.force[1], p.force[2] = F[0], F[1], F[2]
+        return p
+
+    def step_begin(self, tau=0.8, force=(0.0, 0.0, 0.0), trt=None, store_moments=True):
+        p = self._single_params(tau, force, trt)
+        _check(lib().chimp_step_begin(self.h, C.byref(p), C.c_int(1 if store_moments else 0)))
+
+    def step_end(self):
+        _check(lib().chimp_step_end(self.h))
+
+    def download_mass_change(self, n_labels):
+        out = np.zeros(n_labels)
+        _check(lib().chimp_download_mass_change(self.h, _p(out)))
+        return out
+
+    def set_halo_buffers(self, k, send_ptr, recv_ptr):
+        _check(lib().chimp_set_halo_buffers(self.h, C.c_int(k), C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))
+
+    def halo_stream(self):
+        return lib().chimp_halo_stream(self.h)
+
+    def last_flux_force(self):
+        return float(lib().chimp_last_flux_force(self.h))
+
+    def step_timed(self, n_steps, tau=0.8, force=(0.0, 0.0, 0.0), trt=None):
+        """runs n_steps and returns the device time in ms of the collide-stream launches
+        (CUDA events on the engine's own stream)"""
+        p = SingleParams()
+        p.collision = TRT if trt else BGK
+        p.tau = tau
+        p.tau_sym, p.tau_anti = trt if trt else (0.0, 0.0)
+        F = list(force) + [0.0] * (3 - len(force))
+        p.force[0], p.force[1], p.force[2] = F[0], F[1], F[2]
+        ms = C.c_double()
+        _check(lib().chimp_step_timed(self.h, C.byref(p), C.c_int(n_steps), C.byref(ms)))
+        return ms.value
+
+    # ---- halo / streams -------------------------------------------------------------------
+    def num_neighbors(self):
+        return int(lib().chimp_num_neighbors(self.h))
+
+    def neighbor_info(self, k):
+        rank = C.c_int()
+        ns, nr = C.c_longlong(), C.c_longlong()
+        _check(lib().chimp_neighbor_info(self.h, C.c_int(k), C.byref(rank), C.byref(ns), C.byref(nr)))
+        return rank.value, ns.value, nr.value
+
+    def send_buffer_ptr(self, k):
+        return lib().chimp_send_buffer_dev(self.h, C.c_int(k))
+
+    def recv_buffer_ptr(self, k):
+        return lib().chimp_recv_buffer_dev(self.h, C.c_int(k))
+
+    def set_exchange_callback(self, fn):
+        """fn(stream_ptr:int) -> None is called once per step on the halo stream"""
+        def tramp(_user, stream):
+            try:
+                fn(int(stream) if stream else 0)
+                return 0
+            except Exception as exc:  # pragma: no cover
+                print("exchange callback failed:", exc)
+                return 1
+        self._cb = EXCHANGE_FN(tramp)
+        _check(lib().chimp_set_exchange_callback(self.h, self._cb, None))
+
+    def set_stream(self, ptr):
+        _check(lib().chimp_set_stream(self.h, C.c_void_p(ptr)))
+
+    def synchronize(self):
+        _check(lib().chimp_synchronize(self.h))
+
+    def num_own_nodes(self):
+        return int(lib().chimp_num_own_nodes(self.h))
+
+    def irregular_fraction(self):
+        return float(lib().chimp_irregular_fraction(self.h))
+
+    def index_bytes_per_node(self):
+        return float(lib().chimp_index_bytes_per_node(self.h))
+
+
+def lattice_from_device_table(lattice: str, n_bulk, n_pad, n_halo, table_ptr, label_ptr, n_fields=1,
+                              index_form=INDEX_RANK, device=-1):
+    """structured-ingest path: pull table already resident on the device (int32 [nQ][n_pad])"""
+    obj = Lattice.__new__(Lattice)
+    obj.lattice = lattice
+    obj.nq = len(G.BASIS[lattice])
+    obj.nd = G.BASIS[lattice].shape[1]
+    obj.n_nodes = 0
+    obj.n_fields = n_fields
+    obj._cb = None
+    obj.h = C.c_void_p()
+    _check(lib().chimp_create_from_device_table(C.byref(obj.h), G.LATTICE_ID[lattice], C.c_int(n_bulk), C.c_int(n_pad),
+                                                C.c_int(n_halo), C.c_void_p(table_ptr), C.c_void_p(label_ptr),
+                                                C.c_int(n_fields), C.c_int(index_form), C.c_int(device)))
+    return obj

@@ -1,0 +1,118 @@
+"""Host-side setup of the three target mains, restated from the reference's main() bodies
+(everything that happens before the time loop; the loop itself runs on the GPU).
+
+std_case      src/std_case/main.cpp:62-96          (init_rho attribute, f = w_q * rho)
+std_one_phase src/std_one_phase/main.cpp:27-126, 253-345, 452-474   (tags, link lists, mass-source scale)
+twophase      src/twophase/main_TWOPHASE.cpp:81-87, 150-205        (float32 density attributes, wettability)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import geometry as G
+
+
+def lattice_weights(lattice: str) -> np.ndarray:
+    """w[] of the reference's lattice structs (LBd2q9.h:26-32, LBd3q19.h:25-32; D3Q27 per contract)"""
+    if lattice == "D2Q9":
+        w0, w1, w2 = 16.0 / 36.0, 4.0 / 36.0, 1.0 / 36.0
+        return np.array([w1, w2, w1, w2, w1, w2, w1, w2, w0])
+    if lattice == "D3Q19":
+        w0, w1, w2 = 12.0 / 36.0, 2.0 / 36.0, 1.0 / 36.0
+        return np.array([w1] * 3 + [w2] * 6 + [w1] * 3 + [w2] * 6 + [w0])
+    if lattice == "D3Q27":
+        w0, w1, w2, w3 = 64.0 / 216.0, 16.0 / 216.0, 4.0 / 216.0, 1.0 / 216.0
+        half = [w1] * 3 + [w2] * 6 + [w3] * 4
+        return np.array(half + half + [w0])
+    raise ValueError(lattice)
+
+
+def std_case_initial_state(tab: G.RankTables, init_rho):
+    """f(0,q,n) = w[q]*rho(0,n) on bulk nodes, zero elsewhere (std_case/main.cpp:62-96).
+    Returns f [size, 1, nQ] and rho [size]."""
+    g = tab.g
+    rho = tab.attribute(g.pad_attribute(np.asarray(init_rho, dtype=np.float64)))
+    f = np.zeros((tab.size, 1, g.nq))
+    bulk = tab.bulk_nodes()
+    f[bulk, 0, :] = lattice_weights(g.lattice)[None, :] * rho[bulk, None]
+    return f, rho
+
+
+def one_phase_setup(lg: G.LatticeGeometry, tabs, attrs):
+    """Per rank: node tags, link lists, force switch, interior-domain labels, mass-source
+    markers, and the global 1/count scale per interior domain (main.cpp:253-345, 452-458)."""
+    nqnz = lg.nq - 1
+    pad = {k: lg.pad_attribute(np.asarray(v)) for k, v in attrs.items()}
+    per_rank = []
+    global_max = 0
+    for t in tabs:
+        tags = t.attribute(pad["nodetags"]).astype(np.int64)
+        tags[0] = -1  # Nodes::nodeTag_ default (LBnodes.h:119)
+        interior = t.attribute(pad["interior_domains"]).astype(np.int32)
+        force_on = t.attribute(pad["force"]).astype(np.float64)
+        mine = t.node_rank == t.my_rank
+        mine[0] = False
+        if mine.any():
+            global_max = max(global_max, int(interior[mine].max()))
+        per_rank.append(dict(tags=tags, interior=interior, force_on=force_on, mine=mine))
+    counts = np.zeros(global_max + 1)
+    for t, pr in zip(tabs, per_rank):
+        add = np.zeros(t.size)
+        sel = pr["mine"] & (pr["interior"] > 0) & (pr["tags"] < 3)
+        add[sel] = 1.0
+        pr["add_source"] = add
+        np.add.at(counts, pr["interior"][sel], 1.0)
+    scale = np.zeros(global_max + 1)
+    scale[1:] = 1.0 / counts[1:] if global_max else scale[1:]
+    for t, pr in zip(tabs, per_rank):
+        tags, mine = pr["tags"], pr["mine"]
+        n = np.arange(t.size)
+
+        def links(bit, want, need_phase=None):
+            flagged = mine & (((tags >> bit) & 1) == 1)
+            if need_phase is not None:
+                flagged &= (tags & 3) == need_phase
+            nodes = n[flagged]
+            nb = t.neigh[nodes, :nqnz]
+            hit = (tags[nb] & 3) == want
+            rows, q = np.nonzero(hit)
+            qrev = np.array([G.reverse_direction(lg.lattice, int(x)) for x in range(lg.nq)])
+            return np.stack([nodes[rows], qrev[q], nb[rows, q], q], axis=1).astype(np.int32)
+
+        pr["solid_links"] = links(3, 0)
+        pr["press_links"] = links(4, 3)
+        pr["fluid_links"] = links(2, 2, need_phase=1)
+        pr["scale"] = scale
+        # the initial state: rho = 1, u = 0, f = calcfeq(1, 0, 0) = w_q on bulk (main.cpp:441-474)
+        f = np.zeros((t.size, 1, lg.nq))
+        f[t.bulk_nodes(), 0, :] = lattice_weights(lg.lattice)[None, :]
+        pr["f0"] = f
+    return per_rank
+
+
+def two_phase_setup(lg: G.LatticeGeometry, tabs, rho0, rho1, wettability):
+    """rho(2,size) and f(2,size) at t=0 (main_TWOPHASE.cpp:150-205).  The density attributes are
+    read through `float` there, so values pass through float32 and the wall value 1-val is
+    float32 arithmetic."""
+    p0 = lg.pad_attribute(np.asarray(rho0, dtype=np.float64))
+    p1 = lg.pad_attribute(np.asarray(rho1, dtype=np.float64))
+    pw = lg.pad_attribute(np.asarray(wettability, dtype=np.float64))
+    w = lattice_weights(lg.lattice)
+    out = []
+    for t in tabs:
+        rho = np.zeros((t.size, 2))
+        rho[:, 0] = t.attribute(p0).astype(np.float32).astype(np.float64)
+        rho[:, 1] = t.attribute(p1).astype(np.float32).astype(np.float64)
+        wet = t.attribute(pw).astype(np.float32)
+        sb = t.node_type == 1
+        sb[0] = False
+        rho[sb, 0] = wet[sb].astype(np.float64)
+        rho[sb, 1] = (np.float32(1.0) - wet[sb]).astype(np.float64)
+        rho[0, :] = 0.0
+        f = np.zeros((t.size, 2, lg.nq))
+        bulk = t.bulk_nodes()
+        for fld in range(2):
+            # initiateLbField (LBinitiatefield.h:52-56) with u = 0: w*rho*(1.0 + 0 + 4.5*(0 - 0))
+            f[bulk, fld, :] = (w[None, :] * rho[bulk, fld, None]) * 1.0
+        out.append(dict(rho=rho, f0=f, solid_bnd=t.solid_bnd_nodes()))
+    return out

@@ -23,6 +23,8 @@
 #include "kernels.cuh"
 
 namespace chimp {
+__global__ void massFinalizeKernel(const double *, int, const double *, double *, double *);
+__global__ void fillKernel(double *p, double v, long long count);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint32_t *, int *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *);
 } // namespace chimp
@@ -70,7 +72,10 @@ struct Neighbor {
     std::vector<int32_t> sendNodes, nDirSend, dirSend, recvNodes, nDirRecv, dirRecv;
     long long sendCount = 0, recvCount = 0; // per field
     long long *d_sendSrc = nullptr, *d_recvDst = nullptr;
-    double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
+    double *d_sendBuf = nullptr, *d_recvBuf = nullptr;   // owned
+    double *x_sendBuf = nullptr, *x_recvBuf = nullptr;   // caller-owned overrides (chimp_set_halo_buffers)
+    double *sendBuf() const { return x_sendBuf ? x_sendBuf : d_sendBuf; }
+    double *recvBuf() const { return x_recvBuf ? x_recvBuf : d_recvBuf; }
 };
 
 template <class T>
@@ -93,7 +98,11 @@ struct chimp_lattice {
     std::vector<Op> ops;
     std::vector<Neighbor> nbrs;
     std::vector<int32_t> solidBnd;
-    bool finalized = false;
+    bool finalized = false, hostBuilt = false;
+    // host-built tables (chimp_build_host)
+    std::vector<int32_t> hTable, hLabel;
+    std::vector<uint32_t> hPmask;
+    std::vector<std::vector<long long>> hSendSrc, hRecvDst;
     // device layout
     int n = 0, nPad = 0, nHalo = 0, nBoundary = 0;
     long long stride = 0;
@@ -110,6 +119,7 @@ struct chimp_lattice {
     bool onePhase = false;
     double *d_forceOn = nullptr, *d_addSource = nullptr, *d_srcPerLabel = nullptr, *d_massPartial = nullptr;
     int32_t *d_labelAttr = nullptr;
+    double *d_scale = nullptr, *d_mass = nullptr;
     int nLabels = 0;
     std::vector<double> scalePerLabel;
     double rhoW = 1.0;
@@ -214,6 +224,33 @@ void dispatchSingle(const chimp_lattice *c, const StepArgs &a, int coll, bool mo
 #undef CH_LAUNCH
 }
 
+int massChangePass(chimp_lattice *c, const StepArgs &a);
+
+template <class L>
+void launchMassChange(const chimp_lattice *c, const StepArgs &a, unsigned grid)
+{
+    if (c->indexForm == CHIMP_INDEX_RANK) massChangeKernel<L, IDX_RANK><<<grid, 256, 0, c->stream>>>(a, c->nLabels, c->d_massPartial);
+    else massChangeKernel<L, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a, c->nLabels, c->d_massPartial);
+}
+
+int massChangePass(chimp_lattice *c, const StepArgs &a)
+{
+    if (!c->nbrs.empty()) return fail("mass-conservation source across ranks needs an all-reduce (not wired yet)");
+    const unsigned grid = (unsigned)((c->n + 255) / 256);
+    if (!c->d_massPartial) {
+        CUDA_OK(cudaMalloc(&c->d_massPartial, (size_t)grid * c->nLabels * sizeof(double)));
+    }
+    switch (c->lattice) {
+    case CHIMP_D2Q9: launchMassChange<D2Q9>(c, a, grid); break;
+    case CHIMP_D3Q19: launchMassChange<D3Q19>(c, a, grid); break;
+    case CHIMP_D3Q27: launchMassChange<D3Q27>(c, a, grid); break;
+    }
+    massFinalizeKernel<<<c->nLabels, 256, 0, c->stream>>>(c->d_massPartial, (int)grid, c->d_scale, c->d_mass, c->d_srcPerLabel);
+    g_launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 void dispatchSingleLattice(const chimp_lattice *c, const StepArgs &a, int coll, bool mom, cudaStream_t s)
 {
     switch (c->lattice) {
@@ -264,11 +301,6 @@ int chimp_create(chimp_lattice **out, int lattice, int n_nodes, const int32_t *n
     if (li.nQ == 0) return fail("unknown lattice id %d", lattice);
     if (n_fields < 1 || n_fields > 2) return fail("n_fields must be 1 or 2, got %d", n_fields);
     if (n_nodes < 1 || n_bulk < 0 || !neigh || (!bulk && n_bulk > 0)) return fail("bad table arguments");
-    int nDev = 0;
-    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
-        return fail("no CUDA device available: this engine has no CPU fallback");
-    if (device < 0) CUDA_OK(cudaGetDevice(&device));
-    CUDA_OK(cudaSetDevice(device));
     for (int b = 0; b < n_bulk; ++b) {
         if (bulk[b] <= 0 || bulk[b] >= n_nodes) return fail("bulk[%d]=%d outside (0,%d)", b, bulk[b], n_nodes);
         if (b && bulk[b] <= bulk[b - 1]) return fail("bulk list must be strictly ascending (LBgeometry.h:11-21)");
@@ -283,7 +315,6 @@ int chimp_create(chimp_lattice **out, int lattice, int n_nodes, const int32_t *n
     c->nNodes = n_nodes;
     c->neigh.assign(neigh, neigh + (size_t)n_nodes * li.nQ);
     c->bulk.assign(bulk, bulk + n_bulk);
-    if (setupStreams(c)) { delete c; return 1; }
     *out = c;
     return 0;
 }
@@ -357,11 +388,10 @@ int chimp_set_solid_boundary(chimp_lattice *c, int n_solid, const int32_t *solid
     return 0;
 }
 
-int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
+int chimp_build_host(chimp_lattice *c, int boundary_first)
 {
     if (check(c, false)) return 1;
-    if (index_form != CHIMP_INDEX_TABLE && index_form != CHIMP_INDEX_RANK) return fail("unknown index form %d", index_form);
-    CUDA_OK(cudaSetDevice(c->device));
+    if (c->hostBuilt) return fail("host tables already built");
     const LatInfo li = c->li;
     const int nQ = li.nQ;
     const int nBulk = (int)c->bulk.size();
@@ -500,18 +530,15 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
             table[(size_t)q * c->nPad + i] = t;
         }
     }
-    // 6. upload
-    CUDA_OK(cudaMalloc(&c->d_table, table.size() * sizeof(int32_t)));
-    CUDA_OK(cudaMemcpy(c->d_table, table.data(), table.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMalloc(&c->d_label, label.size() * sizeof(int32_t)));
-    CUDA_OK(cudaMemcpy(c->d_label, label.data(), label.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMalloc(&c->d_pmask, pmask.size() * sizeof(uint32_t)));
-    CUDA_OK(cudaMemcpy(c->d_pmask, pmask.data(), pmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    // halo lists (slot offsets inside one field's planes)
+    // 6. halo lists (slot offsets inside one field's planes)
     long long haloOff = 0;
+    c->hSendSrc.resize(c->nbrs.size());
+    c->hRecvDst.resize(c->nbrs.size());
     for (size_t k = 0; k < c->nbrs.size(); ++k) {
         Neighbor &nb = c->nbrs[k];
-        std::vector<long long> src(sendSrc[k].size()), dst((size_t)nb.recvCount);
+        std::vector<long long> &src = c->hSendSrc[k], &dst = c->hRecvDst[k];
+        src.resize(sendSrc[k].size());
+        dst.resize((size_t)nb.recvCount);
         for (size_t e = 0; e < src.size(); ++e) {
             const long long q = sendSrc[k][e] / nBulk, b = sendSrc[k][e] % nBulk;
             src[e] = q * c->stride + devOf[b];
@@ -521,6 +548,39 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
             dst[e] = (long long)qh.first * c->stride + c->nPad + qh.second;
         }
         haloOff += nb.recvCount;
+    }
+    c->hTable.swap(table);
+    c->hLabel.swap(label);
+    c->hPmask.swap(pmask);
+    // release host inputs
+    std::vector<int32_t>().swap(c->neigh);
+    std::vector<Op>().swap(c->ops);
+    c->hostBuilt = true;
+    return 0;
+}
+
+int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
+{
+    if (check(c, false)) return 1;
+    if (index_form != CHIMP_INDEX_TABLE && index_form != CHIMP_INDEX_RANK) return fail("unknown index form %d", index_form);
+    if (!c->hostBuilt && chimp_build_host(c, boundary_first)) return 1;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+        return fail("no CUDA device available: this engine has no CPU fallback");
+    if (c->device < 0) CUDA_OK(cudaGetDevice(&c->device));
+    CUDA_OK(cudaSetDevice(c->device));
+    if (setupStreams(c)) return 1;
+    const std::vector<int32_t> &table = c->hTable, &label = c->hLabel;
+    const std::vector<uint32_t> &pmask = c->hPmask;
+    CUDA_OK(cudaMalloc(&c->d_table, table.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpy(c->d_table, table.data(), table.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_label, label.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpy(c->d_label, label.data(), label.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_pmask, pmask.size() * sizeof(uint32_t)));
+    CUDA_OK(cudaMemcpy(c->d_pmask, pmask.data(), pmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    for (size_t k = 0; k < c->nbrs.size(); ++k) {
+        Neighbor &nb = c->nbrs[k];
+        const std::vector<long long> &src = c->hSendSrc[k], &dst = c->hRecvDst[k];
         if (!src.empty()) {
             CUDA_OK(cudaMalloc(&nb.d_sendSrc, src.size() * sizeof(long long)));
             CUDA_OK(cudaMemcpy(nb.d_sendSrc, src.data(), src.size() * sizeof(long long), cudaMemcpyHostToDevice));
@@ -536,9 +596,6 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
     if (index_form == CHIMP_INDEX_RANK && buildRankIndex(c)) return 1;
     if (allocateState(c)) return 1;
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    // release host inputs
-    std::vector<int32_t>().swap(c->neigh);
-    std::vector<Op>().swap(c->ops);
     c->finalized = true;
     return 0;
 }
@@ -565,6 +622,7 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
     c->nFields = n_fields;
     if (setupStreams(c)) { delete c; return 1; }
     c->n = n_bulk;
+    c->nNodes = n_bulk + 1; // labels 1..N are the leading rows of the reference's LbField (fluid nodes come first, vtklb.py:92-94)
     c->nPad = n_pad;
     c->nHalo = n_halo;
     c->stride = (long long)n_pad + n_halo;
@@ -573,6 +631,7 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
     CUDA_OK(cudaMemcpyAsync(c->d_table, table_dev, tb, cudaMemcpyDeviceToDevice, c->stream));
     CUDA_OK(cudaMalloc(&c->d_label, (size_t)n_pad * sizeof(int32_t)));
     CUDA_OK(cudaMemcpyAsync(c->d_label, label_dev, (size_t)n_pad * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    c->hostBuilt = true;
     c->indexForm = index_form;
     if (index_form == CHIMP_INDEX_RANK && buildRankIndex(c)) { chimp_destroy(c); return 1; }
     if (allocateState(c)) { chimp_destroy(c); return 1; }
@@ -591,7 +650,7 @@ void chimp_destroy(chimp_lattice *c)
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
     freeDev(c->d_rho); freeDev(c->d_vel);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
-    freeDev(c->d_labelAttr);
+    freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
     for (auto &nb : c->nbrs) { freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf); }
     if (c->evBoundary) cudaEventDestroy(c->evBoundary);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
@@ -725,6 +784,11 @@ int chimp_set_one_phase_attributes(chimp_lattice *c, const double *force_on, con
     CUDA_OK(cudaMemcpy(c->d_labelAttr, lab.data(), lab.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&c->d_srcPerLabel, (size_t)n_labels * sizeof(double)));
     CUDA_OK(cudaMemset(c->d_srcPerLabel, 0, (size_t)n_labels * sizeof(double)));
+    freeDev(c->d_scale); freeDev(c->d_mass); freeDev(c->d_massPartial);
+    CUDA_OK(cudaMalloc(&c->d_scale, (size_t)n_labels * sizeof(double)));
+    CUDA_OK(cudaMemcpy(c->d_scale, scale_per_label, (size_t)n_labels * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_mass, (size_t)n_labels * sizeof(double)));
+    CUDA_OK(cudaMemset(c->d_mass, 0, (size_t)n_labels * sizeof(double)));
     c->nLabels = n_labels;
     c->scalePerLabel.assign(scale_per_label, scale_per_label + n_labels);
     c->rhoW = rho_w;
@@ -733,15 +797,15 @@ int chimp_set_one_phase_attributes(chimp_lattice *c, const double *force_on, con
 }
 
 // ---- stepping -----------------------------------------------------------------------------
-int chimp_step_single(chimp_lattice *c, const chimp_single_params *p, int n_steps)
+namespace {
+
+int fillStepArgs(chimp_lattice *c, const chimp_single_params *p, StepArgs &a)
 {
-    if (check(c, true)) return 1;
     if (!p) return fail("params is null");
     if (c->nFields != 1) return fail("chimp_step_single needs a one-field lattice");
     if (p->collision != CHIMP_BGK && p->collision != CHIMP_TRT) return fail("unknown collision %d", p->collision);
     if (c->hasPressure && !c->onePhase) return fail("pressure links need chimp_set_one_phase_attributes");
-    CUDA_OK(cudaSetDevice(c->device));
-    StepArgs a{};
+    a = StepArgs{};
     a.stride = c->stride;
     a.n = c->n;
     a.nPad = c->nPad;
@@ -768,46 +832,149 @@ int chimp_step_single(chimp_lattice *c, const chimp_single_params *p, int n_step
     a.rhoW = c->rhoW;
     a.rho = c->d_rho;
     a.vel = c->d_vel;
-    const bool multi = !c->nbrs.empty();
-    for (int s = 0; s < n_steps; ++s) {
-        const bool mom = (s == n_steps - 1);
-        a.fin = c->d_f[c->cur];
-        a.fout = c->d_f[c->cur ^ 1];
-        if (c->onePhase && c->nLabels > 1) return fail("mass-conservation source with interior domains is not implemented yet");
-        if (!multi) {
-            a.begin = 0;
-            a.end = c->n;
-            dispatchSingleLattice(c, a, p->collision, mom, c->stream);
-        } else {
-            // halo-coupled nodes first; their packed populations travel while the interior runs
-            a.begin = 0;
-            a.end = c->nBoundary ? std::min(c->nBoundary, c->n) : c->n;
-            dispatchSingleLattice(c, a, p->collision, mom, c->stream);
-            for (auto &nb : c->nbrs)
-                if (nb.sendCount) {
-                    haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.d_sendBuf, a.fout, nb.d_sendSrc, (int)nb.sendCount);
-                    ++g_launches;
-                }
-            CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
-            CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
-            if (c->exchange && c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
-            for (auto &nb : c->nbrs)
-                if (nb.recvCount) {
-                    haloUnpackKernel<<<(unsigned)((nb.recvCount + 255) / 256), 256, 0, c->haloStream>>>(a.fout, nb.d_recvBuf, nb.d_recvDst, (int)nb.recvCount);
-                    ++g_launches;
-                }
-            CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
-            if (c->nBoundary && c->nBoundary < c->n) {
-                a.begin = c->nBoundary;
-                a.end = c->n;
-                dispatchSingleLattice(c, a, p->collision, mom, c->stream);
-            }
-            CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
+    return 0;
+}
+
+// first half of an iteration: collide + stream of all own nodes, halo-coupled nodes first, and
+// packing of the populations the neighbour ranks will pull
+int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom)
+{
+    StepArgs a;
+    if (fillStepArgs(c, p, a)) return 1;
+    a.fin = c->d_f[c->cur];
+    a.fout = c->d_f[c->cur ^ 1];
+    if (c->onePhase && c->nLabels > 1 && massChangePass(c, a)) return 1;
+    if (c->nbrs.empty()) {
+        a.begin = 0;
+        a.end = c->n;
+        dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+        return 0;
+    }
+    a.begin = 0;
+    a.end = c->nBoundary ? c->nBoundary : c->n;
+    dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+    for (auto &nb : c->nbrs)
+        if (nb.sendCount) {
+            haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.sendBuf(), a.fout, nb.d_sendSrc, (int)nb.sendCount);
+            ++g_launches;
         }
-        c->cur ^= 1;
-        ++c->steps;
+    CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+    if (c->nBoundary && c->nBoundary < c->n) {
+        a.begin = c->nBoundary;
+        a.end = c->n;
+        dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+    }
+    return 0;
+}
+
+// second half: incoming populations go to the halo-in slots of the new buffer; buffers swap
+int stepEnd(chimp_lattice *c)
+{
+    double *fout = c->d_f[c->cur ^ 1];
+    if (!c->nbrs.empty()) {
+        for (auto &nb : c->nbrs)
+            if (nb.recvCount) {
+                haloUnpackKernel<<<(unsigned)((nb.recvCount + 255) / 256), 256, 0, c->haloStream>>>(fout, nb.recvBuf(), nb.d_recvDst, (int)nb.recvCount);
+                ++g_launches;
+            }
+        CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
+        CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
+    }
+    c->cur ^= 1;
+    ++c->steps;
+    return 0;
+}
+
+} // namespace
+
+int chimp_step_begin(chimp_lattice *c, const chimp_single_params *p, int store_moments)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    if (stepBegin(c, p, store_moments != 0)) return 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int chimp_step_end(chimp_lattice *c)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    if (stepEnd(c)) return 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int chimp_step_single(chimp_lattice *c, const chimp_single_params *p, int n_steps)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    for (int s = 0; s < n_steps; ++s) {
+        if (stepBegin(c, p, s == n_steps - 1)) return 1;
+        if (!c->nbrs.empty() && c->exchange && c->exchange(c->exchangeUser, (void *)c->haloStream))
+            return fail("exchange callback failed");
+        if (stepEnd(c)) return 1;
     }
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int chimp_step_timed(chimp_lattice *c, const chimp_single_params *p, int n_steps, double *ms)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, c->stream));
+    const int rc = chimp_step_single(c, p, n_steps);
+    CUDA_OK(cudaEventRecord(e1, c->stream));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float t = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = t;
+    return rc;
+}
+
+int chimp_init_uniform(chimp_lattice *c, double rho)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    std::vector<double> wq(c->li.nQ);
+    for (int q = 0; q < c->li.nQ; ++q) wq[q] = chimp_lattice_w(c->lattice, q) * rho;
+    for (int f = 0; f < c->nFields; ++f)
+        for (int q = 0; q < c->li.nQ; ++q) {
+            const long long count = c->stride;
+            fillKernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(c->d_f[c->cur] + ((long long)f * c->li.nQ + q) * c->stride, wq[q], count);
+            ++g_launches;
+        }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int chimp_download_moments_device_order(chimp_lattice *c, double *rho, double *vel)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (rho) CUDA_OK(cudaMemcpy(rho, c->d_rho, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (vel)
+        for (int d = 0; d < c->li.nD; ++d)
+            CUDA_OK(cudaMemcpy(vel + (size_t)d * c->n, c->d_vel + (size_t)d * c->nPad, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int chimp_download_mass_change(chimp_lattice *c, double *mass_per_label)
+{
+    if (check(c, true)) return 1;
+    if (!c->onePhase) return fail("one-phase attributes not set");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaMemcpy(mass_per_label, c->d_mass, (size_t)c->nLabels * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -826,8 +993,16 @@ int chimp_neighbor_info(chimp_lattice *c, int k, int *neig_rank, long long *send
     if (recv_count) *recv_count = c->nbrs[k].recvCount * c->nFields;
     return 0;
 }
-void *chimp_send_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].d_sendBuf : nullptr; }
-void *chimp_recv_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].d_recvBuf : nullptr; }
+void *chimp_send_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].sendBuf() : nullptr; }
+void *chimp_recv_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].recvBuf() : nullptr; }
+int chimp_set_halo_buffers(chimp_lattice *c, int k, void *send_dev, void *recv_dev)
+{
+    if (!c || k < 0 || k >= (int)c->nbrs.size()) return fail("bad neighbour index");
+    c->nbrs[k].x_sendBuf = (double *)send_dev;
+    c->nbrs[k].x_recvBuf = (double *)recv_dev;
+    return 0;
+}
+void *chimp_halo_stream(chimp_lattice *c) { return c ? (void *)c->haloStream : nullptr; }
 int chimp_set_exchange_callback(chimp_lattice *c, chimp_exchange_fn fn, void *user)
 {
     if (!c) return fail("null lattice handle");
@@ -854,13 +1029,27 @@ int chimp_synchronize(chimp_lattice *c)
 
 // ---- introspection ------------------------------------------------------------------------
 int chimp_num_own_nodes(chimp_lattice *c) { return c ? c->n : 0; }
-int chimp_download_pull_table(chimp_lattice *c, int32_t *table, int32_t *labels)
+int chimp_host_table_info(chimp_lattice *c, long long *info6)
 {
-    if (check(c, true)) return 1;
-    CUDA_OK(cudaSetDevice(c->device));
+    if (!c || !c->hostBuilt) return fail("host tables not built");
+    info6[0] = c->n; info6[1] = c->nPad; info6[2] = c->nHalo; info6[3] = c->stride; info6[4] = c->nBoundary; info6[5] = 0;
+    return 0;
+}
+int chimp_host_table(chimp_lattice *c, int32_t *table, int32_t *labels, uint32_t *pmask)
+{
+    if (!c || !c->hostBuilt) return fail("host tables not built");
     for (int q = 0; q < c->li.nQ; ++q)
-        CUDA_OK(cudaMemcpy(table + (size_t)q * c->n, c->d_table + (size_t)q * c->nPad, (size_t)c->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(labels, c->d_label, (size_t)c->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        memcpy(table + (size_t)q * c->n, c->hTable.data() + (size_t)q * c->nPad, (size_t)c->n * sizeof(int32_t));
+    memcpy(labels, c->hLabel.data(), (size_t)c->n * sizeof(int32_t));
+    memcpy(pmask, c->hPmask.data(), (size_t)c->n * sizeof(uint32_t));
+    return 0;
+}
+int chimp_host_halo_lists(chimp_lattice *c, int k, long long *send_src, long long *recv_dst)
+{
+    if (!c || !c->hostBuilt) return fail("host tables not built");
+    if (k < 0 || k >= (int)c->nbrs.size()) return fail("bad neighbour index");
+    if (!c->hSendSrc[k].empty()) memcpy(send_src, c->hSendSrc[k].data(), c->hSendSrc[k].size() * sizeof(long long));
+    if (!c->hRecvDst[k].empty()) memcpy(recv_dst, c->hRecvDst[k].data(), c->hRecvDst[k].size() * sizeof(long long));
     return 0;
 }
 double chimp_irregular_fraction(chimp_lattice *c)

@@ -26,6 +26,26 @@ __global__ void haloUnpackKernel(double *X, const double *__restrict__ buf, cons
     if (k < count) X[dst[k]] = buf[k];
 }
 
+__global__ void fillKernel(double *p, double v, long long count)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) p[k] = v;
+}
+
+__global__ void massFinalizeKernel(const double *__restrict__ partial, int nBlocks, const double *__restrict__ scale,
+                                   double *mass, double *src)
+{
+    __shared__ double sh[8];
+    const int l = blockIdx.x;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nBlocks; b += blockDim.x) v += partial[(long long)l * nBlocks + b];
+    const double s = blockSum256(v, sh);
+    if (threadIdx.x == 0) {
+        mass[l] = s;
+        src[l] = 0.9 * 2 * scale[l] * s;
+    }
+}
+
 // ---- index compression (IDX_RANK) ------------------------------------------------------
 // One warp per (tile, q).  A pair is regular when every non-bounce lane l satisfies
 // T[q][32*tile + l] == base + (number of non-bounce lanes below l).

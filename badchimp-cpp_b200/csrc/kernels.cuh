@@ -100,7 +100,7 @@ struct Gather {
             const unsigned below = (1u << lane) - 1u;
 #pragma unroll
             for (int q = 0; q < L::nQ; ++q) {
-                const int b = __ldg(a.idx.base + (long long)q * a.idx.nTiles + tile);
+                const int b = tile < a.idx.nTiles ? __ldg(a.idx.base + (long long)q * a.idx.nTiles + tile) : 0;
                 const unsigned bb = __ballot_sync(0xffffffffu, (m >> q) & 1u);
                 int s;
                 if (b >= 0) s = b + __popc(~bb & below);
@@ -189,6 +189,48 @@ __global__ void __launch_bounds__(256) collideStreamKernel(const StepArgs a)
 #pragma unroll
     for (int q = 0; q < L::nQ; ++q) a.fout[(long long)q * a.stride + i] = out[q];
 }
+
+// ---------------------------------------------------------------------------------------
+// Per-label sum of (1 - rho) over the own nodes (std_one_phase/main.cpp:520-528) as a
+// fixed-shape tree: warp shuffles, 8 warps per block, one partial per (label, block); the
+// second kernel folds the partials in a fixed order, so the result is run-to-run
+// deterministic (it differs from the reference's sequential sum only by rounding order).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double blockSum256(double v, double *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w];
+    }
+    return t; // valid in thread 0
+}
+
+template <class L, int IDX>
+__global__ void __launch_bounds__(256) massChangeKernel(const StepArgs a, int nLabels, double *partial)
+{
+    __shared__ double sh[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    double f[L::nQ];
+    Gather<L, IDX>::load(a, a.fin, live ? i : 0, live, f);
+    const double val = live ? 1.0 - nodeRho<L>(f) : 0.0;
+    const int lab = live ? a.label[i] : -1;
+    for (int l = 0; l < nLabels; ++l) {
+        const double s = blockSum256(lab == l ? val : 0.0, sh);
+        if (threadIdx.x == 0) partial[(long long)l * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// one block per label: mass[l] = sum of partials; src[l] = 0.9*2*scale[l]*mass[l] (main.cpp:548)
+__global__ void massFinalizeKernel(const double *__restrict__ partial, int nBlocks, const double *__restrict__ scale,
+                                   double *mass, double *src);
 
 // ---------------------------------------------------------------------------------------
 // Layout conversion between the reference AoS field (LBfield.h:300:

@@ -1,0 +1,95 @@
+"""Structured geometry ingest on the device: voxel array -> pull table, without the
+vtklb.py -> ASCII -> LBvtk detour (the reference loader cannot read
+files > 2 GiB, LBvtk.h:194-201, so 512^3 cases are unreachable through it).
+
+The numbering is the reference's: own fluid nodes are labelled 1..N in C-order of geo[x,y,z]
+(vtklb.py:92-94), device slot i = label - 1.  For std_case semantics (half-way bounce back on
+every fluid node that touches a solid, LBhalfwaybb.h:37-63) the pull table is
+    T[q][i] = label(pos_i - c_q) - 1      if that cell is fluid
+            = -1                          otherwise (own reversed slot).
+tests/test_ingest.py checks it against the generic host builder (chimp_build_host) on the
+golden geometries.  torch is used as device-memory plumbing only (cumsum / roll / gather).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import geometry as G
+
+
+def build_pull_table(fluid: torch.Tensor, lattice: str, periodic: str = "xyz"):
+    """fluid: bool/uint8 tensor [nx, ny(, nz)] (True = fluid), single rank.
+    Returns (table int32 [nQ, n_pad], labels int32 [n_pad], n, n_pad) on fluid.device.
+    Non-periodic axes are treated as closed (cells outside the array are solid)."""
+    basis = G.BASIS[lattice]
+    nq, nd = basis.shape
+    assert fluid.dim() == nd
+    fluid = fluid.bool()
+    flat = fluid.reshape(-1)
+    n = int(flat.sum().item())
+    n_pad = ((n + 31) // 32) * 32
+    label = (torch.cumsum(flat, 0, dtype=torch.int32) * flat).reshape(fluid.shape)
+    own = torch.nonzero(flat).reshape(-1)
+    table = torch.full((nq, n_pad), -1, dtype=torch.int32, device=fluid.device)
+    dims = tuple(range(nd))
+    for q in range(nq):
+        c = [int(x) for x in basis[q]]
+        up = torch.roll(label, shifts=c, dims=dims) if any(c) else label
+        if any(c):
+            for ax, name in enumerate("xyz"[:nd]):
+                if name in periodic.lower() or c[ax] == 0:
+                    continue
+                sl = [slice(None)] * nd
+                sl[ax] = 0 if c[ax] > 0 else -1
+                up = up.clone() if up is label else up
+                up[tuple(sl)] = 0
+        table[q, :n] = up.reshape(-1)[own] - 1
+        del up
+    labels = torch.zeros(n_pad, dtype=torch.int32, device=fluid.device)
+    labels[:n] = torch.arange(1, n + 1, dtype=torch.int32, device=fluid.device)
+    return table, labels, n, n_pad
+
+
+def sphere_pack_slab(shape, radius, porosity, seed, z0, z1):
+    """the z-range [z0, z1) of geometry.sphere_pack(shape, ...) without building the whole array;
+    z indices wrap periodically, so z0 = -1 / z1 = nz + 1 give the halo layers."""
+    shape = tuple(int(s) for s in shape)
+    nd = len(shape)
+    vol = float(np.prod(shape))
+    vs = np.pi * radius ** 2 if nd == 2 else 4.0 / 3.0 * np.pi * radius ** 3
+    n_sph = max(1, int(round(-np.log(porosity) * vol / vs)))
+    rng = np.random.default_rng(seed)
+    centres = rng.random((n_sph, nd)) * np.array(shape)
+    nzs = z1 - z0
+    geo = np.ones(shape[:-1] + (nzs,), dtype=np.uint8)
+    r = int(np.ceil(radius)) + 1
+    off = np.arange(-r, r + 1)
+    nz = shape[-1]
+    for c in centres:
+        base = np.floor(c).astype(np.int64)
+        zs = base[-1] + off
+        # slab-local index of each candidate z (periodic images considered)
+        hits = []
+        for shift in (-nz, 0, nz):
+            zl = zs + shift - z0
+            ok = (zl >= 0) & (zl < nzs)
+            if ok.any():
+                hits.append((zs[ok], zl[ok]))
+        if not hits:
+            continue
+        idx = [(base[d] + off) for d in range(nd - 1)]
+        d2xy = None
+        for d in range(nd - 1):
+            dd = (idx[d] - c[d]) ** 2
+            sh = [1] * nd
+            sh[d] = -1
+            d2xy = dd.reshape(sh) if d2xy is None else d2xy + dd.reshape(sh)
+        for zg, zl in hits:
+            dz = ((zg - c[-1]) ** 2).reshape([1] * (nd - 1) + [-1])
+            inside = (d2xy + dz) < radius ** 2
+            sub = np.ix_(*([np.mod(idx[d], shape[d]) for d in range(nd - 1)] + [zl]))
+            block = geo[sub]
+            block[inside] = 0
+            geo[sub] = block
+    return geo

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the fused collide-and-stream hot path (see DESIGN.md, section Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
+
+One "step" = one full iteration (collide, stream, halo, boundary) over the whole lattice.
+Workload at N=1: D3Q19 BGK + Guo force + half-way bounce back in a periodic random sphere
+pack (porosity ~0.35, sphere radius size/8, seed 1234), BASELINE.json configs[2] geometry run
+with the std_case physics of configs[0]; MLUPS counts fluid nodes only.
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--size", type=int, default=0, help="edge length of the cubic sphere pack (0 = default)")
+    ap.add_argument("--index", default="rank", choices=["rank", "table"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import helpers
+    helpers.load_package()
+    import importlib
+    bench_impl = importlib.import_module("badchimp_cpp_b200.bench_impl")
+    if args.impl == "reference":
+        bench_impl.run_reference(args)
+    else:
+        bench_impl.run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,16 @@ int chimp_add_neighbor(chimp_lattice *, int neig_rank, int n_send, const int32_t
  * LBgeometry.h:37-45) carry a constant colour value derived from the wettability densities. */
 int chimp_set_solid_boundary(chimp_lattice *, int n_solid, const int32_t *solid_nodes);
 
+/* host half of the build: symbolic replay of one reference iteration -> pull table and halo
+ * lists.  Pure host code (no CUDA call); chimp_finalize runs it if it has not been run. */
+int chimp_build_host(chimp_lattice *, int boundary_first);
+/* host tables for inspection: info6 = {n_own, n_pad, n_halo, plane_stride, n_boundary, 0};
+ * table int32 [nQ][n_own] (source slot, -1 = reversed own slot), labels [n_own], pmask [n_own];
+ * halo lists of neighbour k as slot offsets q*plane_stride + slot. */
+int chimp_host_table_info(chimp_lattice *, long long *info6);
+int chimp_host_table(chimp_lattice *, int32_t *table, int32_t *labels, uint32_t *pmask);
+int chimp_host_halo_lists(chimp_lattice *, int k, long long *send_src, long long *recv_dst);
+
 /* builds the device tables; index_form is CHIMP_INDEX_TABLE or CHIMP_INDEX_RANK.
  * boundary_first != 0 orders halo-coupled nodes first so that their step can overlap. */
 int chimp_finalize(chimp_lattice *, int index_form, int boundary_first);
@@ -108,6 +118,20 @@ typedef struct {
     double force[3];        /* bodyForce(0,0) */
 } chimp_single_params;
 int chimp_step_single(chimp_lattice *, const chimp_single_params *, int n_steps);
+/* the two halves of one iteration, for hosts that move the halos themselves between them:
+ * begin = collide/stream of all own nodes + packing of outgoing populations (LBmonlatmpi.h:244-252),
+ * end   = unpacking of incoming ones (LBmonlatmpi.h:259-267) + buffer swap (LBfield.h:359) */
+int chimp_step_begin(chimp_lattice *, const chimp_single_params *, int store_moments);
+int chimp_step_end(chimp_lattice *);
+/* massChange[label] of the last step (std_one_phase/main.cpp:528) */
+int chimp_download_mass_change(chimp_lattice *, double *mass_per_label);
+/* same, bracketed by CUDA events on the engine's stream; *ms = device time of the n_steps */
+int chimp_step_timed(chimp_lattice *, const chimp_single_params *, int n_steps, double *ms);
+/* state f_q(n) = w_q * rho for every own node (std_case/main.cpp:92-96 with constant rho);
+ * works for lattices created from device tables, where no reference-layout upload exists */
+int chimp_init_uniform(chimp_lattice *, double rho);
+/* rho [n_own] and vel [nD][n_own] of the last step, in device node order */
+int chimp_download_moments_device_order(chimp_lattice *, double *rho, double *vel);
 
 /* twophase/main_TWOPHASE.cpp:236-392 (colour gradient, 2 fields, flux-controlled force) */
 typedef struct {
@@ -128,6 +152,9 @@ int chimp_neighbor_info(chimp_lattice *, int k, int *neig_rank, long long *send_
 /* device pointers of the packed send / recv buffers of neighbour k (doubles, per field contiguous) */
 void *chimp_send_buffer_dev(chimp_lattice *, int k);
 void *chimp_recv_buffer_dev(chimp_lattice *, int k);
+/* let the engine pack into / unpack from caller-owned device buffers (e.g. torch tensors used with NCCL) */
+int chimp_set_halo_buffers(chimp_lattice *, int k, void *send_dev, void *recv_dev);
+void *chimp_halo_stream(chimp_lattice *);
 typedef int (*chimp_exchange_fn)(void *user, void *stream);
 /* called once per step after the boundary nodes were packed, on the halo stream */
 int chimp_set_exchange_callback(chimp_lattice *, chimp_exchange_fn fn, void *user);
@@ -137,7 +164,6 @@ int chimp_synchronize(chimp_lattice *);
 
 /* ---- introspection for tests / bench */
 int chimp_num_own_nodes(chimp_lattice *);
-int chimp_download_pull_table(chimp_lattice *, int32_t *table /* [nQ][n_own] */, int32_t *labels /* [n_own] */);
 /* fraction of (tile, q) pairs that needed explicit rows in CHIMP_INDEX_RANK form */
 double chimp_irregular_fraction(chimp_lattice *);
 /* device bytes of index data read per node per step, and of population data */

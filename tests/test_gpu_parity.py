@@ -1,0 +1,201 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI
+(libchimp_b200.so via ctypes).  Bars: populations, rho and vel BIT-EXACT against the golden
+dumps of the unmodified reference and against the oracle port on larger seeded cases (the
+kernels are built with -fmad=false and keep the reference's operation order); the cases
+whose global sums are reduced in a different order on the GPU state their tolerance."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+from test_builder_host import build_engine_tables
+
+pytestmark = pytest.mark.gpu
+
+STD = [n for n in helpers.all_golden_names() if n.startswith(("std_", "trt_"))]
+
+
+class InProcessRanks:
+    """N ranks as N engine contexts on one GPU; the halo transport between the two halves of an
+    iteration is a device-to-device copy of the packed buffers (stand-in for NCCL send/recv)."""
+
+    def __init__(self, lats):
+        self.lats = lats
+        self.rt = C.CDLL("libcudart.so")
+        self.rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+
+    def step(self, n, **kw):
+        for _ in range(n):
+            for lat in self.lats:
+                lat.step_begin(**kw)
+            for lat in self.lats:
+                lat.synchronize()
+            for r, lat in enumerate(self.lats):
+                for k in range(lat.num_neighbors()):
+                    nr, ns, nrecv = lat.neighbor_info(k)
+                    other = self.lats[nr]
+                    ko = [j for j in range(other.num_neighbors()) if other.neighbor_info(j)[0] == r][0]
+                    assert other.neighbor_info(ko)[1] == nrecv
+                    if nrecv:
+                        assert self.rt.cudaMemcpy(lat.recv_buffer_ptr(k), other.send_buffer_ptr(ko), nrecv * 8, 3) == 0
+            for lat in self.lats:
+                lat.step_end()
+            for lat in self.lats:
+                lat.synchronize()
+
+
+@pytest.mark.parametrize("index_form", [0, 1])
+@pytest.mark.parametrize("name", [n for n in STD if helpers.Golden(n).nranks == 1])
+def test_std_case_single_rank_bit_exact_vs_reference(name, index_form):
+    g = helpers.Golden(name)
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    lats = build_engine_tables(g, lg, tabs, False)
+    lat, t = lats[0], tabs[0]
+    lat.finalize(index_form)
+    lat.upload(pkg.cases.std_case_initial_state(t, g.attr("init_rho"))[0])
+    a = g.args
+    trt = tuple(a["trt"]) if "trt" in a else None
+    done = 0
+    bulk = t.bulk_nodes()
+    for step in [s for s in g.dump if s > 0]:
+        lat.step_single(step - done, tau=a.get("tau", 0.8), force=g.force(), trt=trt)
+        done = step
+        assert np.array_equal(lat.download()[bulk], g.f(0, step)[bulk]), "f differs at step %d" % step
+        assert np.array_equal(lat.download_rho()[bulk, 0], g.rec(0, "step%d.rho" % step)[bulk])
+        assert np.array_equal(lat.download_vel()[bulk], g.rec(0, "step%d.vel" % step).reshape(t.size, -1)[bulk])
+
+
+@pytest.mark.parametrize("index_form", [0, 1])
+@pytest.mark.parametrize("lattice,shape,periodic", [("D3Q19", (40, 36, 44), "xyz"), ("D3Q27", (30, 28, 26), "xyz"),
+                                                    ("D2Q9", (96, 80), "xy"), ("D3Q19", (32, 30, 28), "")])
+def test_std_case_bit_exact_vs_oracle_port(lattice, shape, periodic, index_form):
+    """larger seeded sphere packs, 25 steps, BGK and TRT, against the oracle port"""
+    pkg = helpers.load_package()
+    port = helpers.oracle_port()
+    geo = pkg.geometry.sphere_pack(shape, min(shape) / 7.0, 0.55, 5).astype(int)
+    if periodic == "":
+        for ax in range(len(shape)):
+            for end in (0, -1):
+                s = [slice(None)] * len(shape)
+                s[ax] = end
+                geo[tuple(s)] = 0
+    lg = pkg.geometry.LatticeGeometry(geo, lattice, periodic)
+    t = lg.all_ranks()[0]
+    rng = np.random.default_rng(2)
+    f0, _ = pkg.cases.std_case_initial_state(t, 1.0 + 0.05 * rng.random(geo.shape))
+    bb = t.halfway_bb(t.fluid_bnd_nodes())
+    bulk = t.bulk_nodes()
+    force = (1e-6, -2e-6, 3e-6)[: lg.nd]
+    for trt in (None, (0.8, 1.125)):
+        lat = pkg.capi.Lattice.from_rank_tables(t)
+        lat.add_halfway_bb(*bb)
+        lat.finalize(index_form)
+        lat.upload(f0)
+        lat.step_single(25, tau=0.7, force=force, trt=trt)
+        ref = port.PortRank(pkg.geometry.LATTICE_ID[lattice], t.neigh, bulk, 1, bb)
+        ref.f[:] = f0
+        ref.step_std_case(25, tau=0.7, force=force, trt=trt)
+        assert np.array_equal(lat.download()[bulk], ref.f[bulk])
+        assert np.array_equal(lat.download_rho()[bulk, 0], ref.rho[bulk, 0])
+        assert np.array_equal(lat.download_vel()[bulk], ref.vel[bulk])
+        if index_form == 1:
+            assert 0.0 <= lat.irregular_fraction() < 0.9
+        lat.close()
+
+
+@pytest.mark.parametrize("boundary_first", [False, True])
+@pytest.mark.parametrize("name", [n for n in STD if helpers.Golden(n).nranks > 1])
+def test_std_case_n_rank_bit_exact_vs_reference(name, boundary_first):
+    """every rank's populations match the reference's N-rank (MPI) run bit for bit"""
+    g = helpers.Golden(name)
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    lats = build_engine_tables(g, lg, tabs, boundary_first)
+    for lat, t in zip(lats, tabs):
+        lat.finalize(1, boundary_first)
+        lat.upload(pkg.cases.std_case_initial_state(t, g.attr("init_rho"))[0])
+    ranks = InProcessRanks(lats)
+    a = g.args
+    done = 0
+    for step in [s for s in g.dump if s > 0]:
+        ranks.step(step - done, tau=a.get("tau", 0.8), force=g.force())
+        done = step
+        for r, (lat, t) in enumerate(zip(lats, tabs)):
+            bulk = t.bulk_nodes()
+            assert np.array_equal(lat.download()[bulk], g.f(r, step)[bulk]), "rank %d step %d" % (r, step)
+            assert np.array_equal(lat.download_rho()[bulk, 0], g.rec(r, "step%d.rho" % step)[bulk])
+
+
+@pytest.mark.parametrize("index_form", [0, 1])
+def test_one_phase_vs_reference(index_form):
+    """std_one_phase loop: masked force, mass-conservation source, solid / anti-bounce-back pressure /
+    fluid-fluid links.  The per-label mass change is a tree sum on the GPU (sequential on the CPU),
+    so the source differs by rounding order: tolerance 1e-12 relative on f, as north_star states;
+    in practice the populations come out bit-identical or within one ulp."""
+    g = helpers.Golden("onephase_d3q19_p1")
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    setup = helpers.one_phase_setup(g, lg, tabs)[0]
+    lat = build_engine_tables(g, lg, tabs, False)[0]
+    t = tabs[0]
+    lat.finalize(index_form)
+    lat.set_one_phase_attributes(setup["force_on"], setup["interior"], setup["add_source"], setup["scale"],
+                                 g.args.get("rhow", 1.0))
+    lat.upload(setup["f0"])
+    bulk = t.bulk_nodes()
+    done = 0
+    for step in [s for s in g.dump if s > 0]:
+        lat.step_single(step - done, tau=g.args["tau"], force=g.force())
+        done = step
+        got, ref = lat.download()[bulk], g.f(0, step)[bulk]
+        assert np.allclose(got, ref, rtol=1e-12, atol=0.0)
+        assert np.allclose(lat.download_rho()[bulk, 0], g.rec(0, "step%d.rho" % step)[bulk], rtol=1e-12, atol=0)
+        assert np.allclose(lat.download_vel()[bulk], g.rec(0, "step%d.vel" % step).reshape(t.size, -1)[bulk],
+                           rtol=1e-9, atol=1e-18)
+        mass = lat.download_mass_change(len(setup["scale"]))
+        assert np.allclose(mass, g.rec(0, "step%d.massChange" % step), rtol=1e-9, atol=1e-16)
+
+
+def test_one_phase_without_interior_domains_is_bit_exact():
+    """with no interior domains the mass source vanishes and no reduction enters: bit-exact vs the oracle"""
+    pkg = helpers.load_package()
+    port = helpers.oracle_port()
+    g = helpers.Golden("onephase_d3q19_p1")
+    lg, tabs = helpers.build_tables(g)
+    attrs = {k: g.attr(k) for k in ("nodetags", "force", "interior_domains")}
+    attrs["interior_domains"] = np.zeros_like(attrs["interior_domains"])
+    setup = pkg.cases.one_phase_setup(lg, tabs, attrs)[0]
+    t = tabs[0]
+    for trt in (None, (0.8, 1.125)):
+        lat = pkg.capi.Lattice.from_rank_tables(t)
+        lat.add_links(pkg.capi.LINK_SOLID, setup["solid_links"])
+        lat.add_links(pkg.capi.LINK_PRESSURE, setup["press_links"])
+        lat.add_links(pkg.capi.LINK_FLUID_SWAP, setup["fluid_links"])
+        lat.finalize(1)
+        lat.set_one_phase_attributes(setup["force_on"], setup["interior"], setup["add_source"], setup["scale"], 1.0)
+        lat.upload(setup["f0"])
+        lat.step_single(12, tau=0.8, force=(0, 0, 1e-5), trt=trt)
+        ref = port.PortRank(1, t.neigh, t.bulk_nodes(), 1)
+        ref.set_one_phase(setup["force_on"], setup["interior"], setup["add_source"], setup["scale"],
+                          setup["solid_links"], setup["press_links"], setup["fluid_links"], 1.0)
+        ref.f[:] = setup["f0"]
+        ref.step_one_phase(12, tau=0.8, force=(0, 0, 1e-5), trt=trt)
+        bulk = t.bulk_nodes()
+        assert np.array_equal(lat.download()[bulk], ref.f[bulk])
+        lat.close()
+
+
+def test_round_trip_upload_download():
+    pkg = helpers.load_package()
+    g = helpers.Golden("std_d3q19_p1")
+    lg, tabs = helpers.build_tables(g)
+    lat = build_engine_tables(g, lg, tabs, False)[0]
+    lat.finalize(1)
+    rng = np.random.default_rng(0)
+    f = rng.random((tabs[0].size, 1, 19))
+    lat.upload(f)
+    out = lat.download()
+    bulk = tabs[0].bulk_nodes()
+    assert np.array_equal(out[bulk], f[bulk])
