@@ -165,7 +165,7 @@ def run_b200(args):
     fluid = torch.from_numpy(geo).to("cuda").bool()
     table, labels, n, n_pad = ingest.build_pull_table(fluid, lattice, "xyz")
     del fluid
-    index_form = capi.INDEX_RANK if args.index == "rank" else capi.INDEX_TABLE
+    index_form = capi.INDEX_COMPACT if args.index == "compact" else capi.INDEX_TABLE
     lat = capi.lattice_from_device_table(lattice, n, n_pad, 0, table.data_ptr(), labels.data_ptr(), 1, index_form, local)
     del table, labels
     torch.cuda.empty_cache()

@@ -14,11 +14,12 @@ import numpy as np
 from . import geometry as G
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchimp_b200.so")
+# CHIMP_LIB selects an alternative build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("CHIMP_LIB") or os.path.join(_HERE, "libchimp_b200.so")
 _lib = None
 
 BGK, TRT = 0, 1
-INDEX_TABLE, INDEX_RANK = 0, 1
+INDEX_TABLE, INDEX_COMPACT = 0, 1
 LINK_SOLID, LINK_PRESSURE, LINK_FLUID_SWAP = 0, 1, 2
 
 
@@ -157,7 +158,7 @@ class Lattice:
         """runs only the host-side table builder (no CUDA); used by the CPU tests"""
         _check(lib().chimp_build_host(self.h, C.c_int(1 if boundary_first else 0)))
 
-    def finalize(self, index_form=INDEX_RANK, boundary_first=False):
+    def finalize(self, index_form=INDEX_COMPACT, boundary_first=False):
         _check(lib().chimp_finalize(self.h, C.c_int(index_form), C.c_int(1 if boundary_first else 0)))
 
     def host_table(self):
@@ -269,6 +270,16 @@ class Lattice:
     def halo_stream(self):
         return lib().chimp_halo_stream(self.h)
 
+    def init_uniform(self, rho=1.0):
+        _check(lib().chimp_init_uniform(self.h, C.c_double(rho)))
+
+    def download_moments_device_order(self):
+        n = self.num_own_nodes()
+        rho = np.zeros(n)
+        vel = np.zeros((self.nd, n))
+        _check(lib().chimp_download_moments_device_order(self.h, _p(rho), _p(vel)))
+        return rho, vel
+
     def last_flux_force(self):
         return float(lib().chimp_last_flux_force(self.h))
 
@@ -330,7 +341,7 @@ class Lattice:
 
 
 def lattice_from_device_table(lattice: str, n_bulk, n_pad, n_halo, table_ptr, label_ptr, n_fields=1,
-                              index_form=INDEX_RANK, device=-1):
+                              index_form=INDEX_COMPACT, device=-1):
     """structured-ingest path: pull table already resident on the device (int32 [nQ][n_pad])"""
     obj = Lattice.__new__(Lattice)
     obj.lattice = lattice

@@ -23,9 +23,10 @@
 #include "kernels.cuh"
 
 namespace chimp {
+__global__ void fluxForceKernel(const double *, int, double, double, double *, double *, int);
 __global__ void massFinalizeKernel(const double *, int, const double *, double *, double *);
 __global__ void fillKernel(double *p, double v, long long count);
-__global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint32_t *, int *);
+__global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *);
 } // namespace chimp
 
@@ -108,13 +109,20 @@ struct chimp_lattice {
     long long stride = 0;
     int indexForm = CHIMP_INDEX_TABLE;
     int32_t *d_table = nullptr, *d_label = nullptr;
-    uint32_t *d_bbmask = nullptr, *d_pmask = nullptr;
+    uint32_t *d_delta = nullptr, *d_pmask = nullptr;
+    int nWords = 0;
     int32_t *d_base = nullptr, *d_rows = nullptr;
     int nTiles = 0, nRows = 0;
     double *d_f[2] = {nullptr, nullptr};
     int cur = 0;
     double *d_rho = nullptr, *d_vel = nullptr;
     bool hasPressure = false;
+    // two-phase (colour gradient)
+    std::vector<int32_t> hPtable;
+    int nPhi = 0, nSolid = 0, nGhost = 0;
+    int32_t *d_ptable = nullptr;
+    double *d_phi = nullptr, *d_fluxPartial = nullptr, *d_fluxSum = nullptr, *d_forceX = nullptr;
+    bool densitySet = false;
     // one-phase attributes
     bool onePhase = false;
     double *d_forceOn = nullptr, *d_addSource = nullptr, *d_srcPerLabel = nullptr, *d_massPartial = nullptr;
@@ -160,15 +168,16 @@ int buildRankIndex(chimp_lattice *c)
 {
     const int nQ = c->li.nQ;
     c->nTiles = c->nPad / 32;
-    CUDA_OK(cudaMalloc(&c->d_bbmask, (size_t)c->nPad * sizeof(uint32_t)));
-    CUDA_OK(cudaMemsetAsync(c->d_bbmask, 0, (size_t)c->nPad * sizeof(uint32_t), c->stream));
+    c->nWords = (nQ + 3) / 4;
+    CUDA_OK(cudaMalloc(&c->d_delta, (size_t)c->nWords * c->nPad * sizeof(uint32_t)));
+    CUDA_OK(cudaMemsetAsync(c->d_delta, 0xff, (size_t)c->nWords * c->nPad * sizeof(uint32_t), c->stream));
     CUDA_OK(cudaMalloc(&c->d_base, (size_t)c->nTiles * nQ * sizeof(int32_t)));
     int *d_cnt = nullptr;
     CUDA_OK(cudaMalloc(&d_cnt, sizeof(int)));
     CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
     const long long threads = (long long)c->nTiles * nQ * 32;
     const unsigned grid = (unsigned)((threads + 255) / 256);
-    classifyTilesKernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->n, c->nPad, nQ, c->nTiles, c->d_base, c->d_bbmask, d_cnt);
+    classifyTilesKernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->n, c->nPad, nQ, c->nTiles, c->d_base, (uint8_t *)c->d_delta, d_cnt);
     ++g_launches;
     CUDA_OK(cudaGetLastError());
     int cnt = 0;
@@ -201,7 +210,7 @@ void launchSingle(const StepArgs &a, bool mom, cudaStream_t s)
 {
     const int count = a.end - a.begin;
     if (count <= 0) return;
-    const int block = 256;
+    const int block = CHIMP_BLOCK;
     const unsigned grid = (unsigned)((count + block - 1) / block);
     if (mom) collideStreamKernel<L, COLL, ONEPHASE, true, IDX><<<grid, block, 0, s>>>(a);
     else collideStreamKernel<L, COLL, ONEPHASE, false, IDX><<<grid, block, 0, s>>>(a);
@@ -212,14 +221,14 @@ template <class L>
 void dispatchSingle(const chimp_lattice *c, const StepArgs &a, int coll, bool mom, cudaStream_t s)
 {
     const bool op = c->onePhase;
-    const bool rk = c->indexForm == CHIMP_INDEX_RANK;
+    const bool rk = c->indexForm == CHIMP_INDEX_COMPACT;
 #define CH_LAUNCH(COLL, OP, IDX) launchSingle<L, COLL, OP, IDX>(a, mom, s)
     if (coll == CHIMP_BGK) {
-        if (op) { if (rk) CH_LAUNCH(COLL_BGK, true, IDX_RANK); else CH_LAUNCH(COLL_BGK, true, IDX_TABLE); }
-        else    { if (rk) CH_LAUNCH(COLL_BGK, false, IDX_RANK); else CH_LAUNCH(COLL_BGK, false, IDX_TABLE); }
+        if (op) { if (rk) CH_LAUNCH(COLL_BGK, true, IDX_COMPACT); else CH_LAUNCH(COLL_BGK, true, IDX_TABLE); }
+        else    { if (rk) CH_LAUNCH(COLL_BGK, false, IDX_COMPACT); else CH_LAUNCH(COLL_BGK, false, IDX_TABLE); }
     } else {
-        if (op) { if (rk) CH_LAUNCH(COLL_TRT, true, IDX_RANK); else CH_LAUNCH(COLL_TRT, true, IDX_TABLE); }
-        else    { if (rk) CH_LAUNCH(COLL_TRT, false, IDX_RANK); else CH_LAUNCH(COLL_TRT, false, IDX_TABLE); }
+        if (op) { if (rk) CH_LAUNCH(COLL_TRT, true, IDX_COMPACT); else CH_LAUNCH(COLL_TRT, true, IDX_TABLE); }
+        else    { if (rk) CH_LAUNCH(COLL_TRT, false, IDX_COMPACT); else CH_LAUNCH(COLL_TRT, false, IDX_TABLE); }
     }
 #undef CH_LAUNCH
 }
@@ -229,7 +238,7 @@ int massChangePass(chimp_lattice *c, const StepArgs &a);
 template <class L>
 void launchMassChange(const chimp_lattice *c, const StepArgs &a, unsigned grid)
 {
-    if (c->indexForm == CHIMP_INDEX_RANK) massChangeKernel<L, IDX_RANK><<<grid, 256, 0, c->stream>>>(a, c->nLabels, c->d_massPartial);
+    if (c->indexForm == CHIMP_INDEX_COMPACT) massChangeKernel<L, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a, c->nLabels, c->d_massPartial);
     else massChangeKernel<L, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a, c->nLabels, c->d_massPartial);
 }
 
@@ -549,6 +558,34 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
         }
         haloOff += nb.recvCount;
     }
+    if (c->nFields == 2) {
+        // phi slots: own nodes, solid-boundary nodes, ghost nodes (in neighbour / list order), one zero slot
+        std::vector<int32_t> slotOf(c->nNodes, -1);
+        for (int b = 0; b < nBulk; ++b) slotOf[c->bulk[b]] = devOf[b];
+        c->nSolid = (int)c->solidBnd.size();
+        for (int k = 0; k < c->nSolid; ++k) {
+            const int node = c->solidBnd[k];
+            if (node <= 0 || node >= c->nNodes) return fail("solid boundary node %d out of range", node);
+            if (slotOf[node] < 0) slotOf[node] = c->nPad + k;
+        }
+        int g = 0;
+        for (auto &nb : c->nbrs)
+            for (int node : nb.recvNodes) {
+                if (slotOf[node] < 0) slotOf[node] = c->nPad + c->nSolid + g;
+                ++g;
+            }
+        c->nGhost = g;
+        const int zeroSlot = c->nPad + c->nSolid + c->nGhost;
+        c->nPhi = zeroSlot + 1;
+        c->hPtable.assign((size_t)nQ * c->nPad, zeroSlot);
+        for (int i = 0; i < nSlots; ++i) {
+            const size_t row = (size_t)c->bulk[order[i]] * nQ;
+            for (int q = 0; q < nQ; ++q) {
+                const int s = slotOf[c->neigh[row + q]];
+                c->hPtable[(size_t)q * c->nPad + i] = s >= 0 ? s : zeroSlot;
+            }
+        }
+    }
     c->hTable.swap(table);
     c->hLabel.swap(label);
     c->hPmask.swap(pmask);
@@ -562,7 +599,7 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
 int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
 {
     if (check(c, false)) return 1;
-    if (index_form != CHIMP_INDEX_TABLE && index_form != CHIMP_INDEX_RANK) return fail("unknown index form %d", index_form);
+    if (index_form != CHIMP_INDEX_TABLE && index_form != CHIMP_INDEX_COMPACT) return fail("unknown index form %d", index_form);
     if (!c->hostBuilt && chimp_build_host(c, boundary_first)) return 1;
     int nDev = 0;
     if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
@@ -592,8 +629,19 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
             CUDA_OK(cudaMalloc(&nb.d_recvBuf, dst.size() * c->nFields * sizeof(double)));
         }
     }
+    if (c->nFields == 2) {
+        CUDA_OK(cudaMalloc(&c->d_ptable, c->hPtable.size() * sizeof(int32_t)));
+        CUDA_OK(cudaMemcpy(c->d_ptable, c->hPtable.data(), c->hPtable.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->d_phi, (size_t)c->nPhi * sizeof(double)));
+        CUDA_OK(cudaMemset(c->d_phi, 0, (size_t)c->nPhi * sizeof(double)));
+        const int nBlocks = (c->n + 255) / 256;
+        CUDA_OK(cudaMalloc(&c->d_fluxPartial, (size_t)std::max(nBlocks, 1) * sizeof(double)));
+        CUDA_OK(cudaMalloc(&c->d_fluxSum, sizeof(double)));
+        CUDA_OK(cudaMalloc(&c->d_forceX, sizeof(double)));
+        CUDA_OK(cudaMemset(c->d_forceX, 0, sizeof(double)));
+    }
     c->indexForm = index_form;
-    if (index_form == CHIMP_INDEX_RANK && buildRankIndex(c)) return 1;
+    if (index_form == CHIMP_INDEX_COMPACT && buildRankIndex(c)) return 1;
     if (allocateState(c)) return 1;
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->finalized = true;
@@ -633,7 +681,7 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
     CUDA_OK(cudaMemcpyAsync(c->d_label, label_dev, (size_t)n_pad * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
     c->hostBuilt = true;
     c->indexForm = index_form;
-    if (index_form == CHIMP_INDEX_RANK && buildRankIndex(c)) { chimp_destroy(c); return 1; }
+    if (index_form == CHIMP_INDEX_COMPACT && buildRankIndex(c)) { chimp_destroy(c); return 1; }
     if (allocateState(c)) { chimp_destroy(c); return 1; }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->finalized = true;
@@ -646,9 +694,10 @@ void chimp_destroy(chimp_lattice *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    freeDev(c->d_table); freeDev(c->d_label); freeDev(c->d_bbmask); freeDev(c->d_pmask);
+    freeDev(c->d_table); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
     freeDev(c->d_rho); freeDev(c->d_vel);
+    freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
     for (auto &nb : c->nbrs) { freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf); }
@@ -810,7 +859,7 @@ int fillStepArgs(chimp_lattice *c, const chimp_single_params *p, StepArgs &a)
     a.n = c->n;
     a.nPad = c->nPad;
     a.idx.table = c->d_table;
-    a.idx.bbmask = c->d_bbmask;
+    a.idx.delta = c->d_delta;
     a.idx.base = c->d_base;
     a.idx.rows = c->d_rows;
     a.idx.nTiles = c->nTiles;
@@ -978,10 +1027,113 @@ int chimp_download_mass_change(chimp_lattice *c, double *mass_per_label)
     return 0;
 }
 
-int chimp_set_twophase_density(chimp_lattice *, const double *) { return fail("twophase path not built yet"); }
-int chimp_step_twophase(chimp_lattice *, const chimp_twophase_params *, int) { return fail("twophase path not built yet"); }
-int chimp_download_phase_field(chimp_lattice *, double *) { return fail("twophase path not built yet"); }
-double chimp_last_flux_force(chimp_lattice *) { return 0.0; }
+int chimp_set_twophase_density(chimp_lattice *c, const double *rho2)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2) return fail("needs a two-field lattice");
+    if (!rho2) return fail("rho is null");
+    CUDA_OK(cudaSetDevice(c->device));
+    // main_TWOPHASE.cpp:280-284: colour of the solid boundary nodes from their (constant) densities
+    std::vector<double> phiWall(std::max(c->nSolid, 1), 0.0);
+    for (int k = 0; k < c->nSolid; ++k) {
+        const double r0 = rho2[2 * (size_t)c->solidBnd[k]], r1 = rho2[2 * (size_t)c->solidBnd[k] + 1];
+        phiWall[k] = (r0 - r1) / (r0 + r1);
+    }
+    if (c->nSolid) CUDA_OK(cudaMemcpy(c->d_phi + c->nPad, phiWall.data(), (size_t)c->nSolid * sizeof(double), cudaMemcpyHostToDevice));
+    c->densitySet = true;
+    return 0;
+}
+
+extern "C++" {
+namespace {
+template <class L>
+void launchTwoPhase(chimp_lattice *c, const TwoPhaseArgs &a, const chimp_twophase_params *p, bool mom, unsigned gridAll)
+{
+    const bool rk = c->indexForm == CHIMP_INDEX_COMPACT;
+    if (rk) phaseMomentsKernel<L, IDX_COMPACT><<<gridAll, 256, 0, c->stream>>>(a);
+    else phaseMomentsKernel<L, IDX_TABLE><<<gridAll, 256, 0, c->stream>>>(a);
+    fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)gridAll, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, 1);
+    const unsigned grid = (unsigned)((a.end - a.begin + 255) / 256);
+    if (rk) {
+        if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a);
+        else twoPhaseCollideKernel<L, false, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a);
+    } else {
+        if (mom) twoPhaseCollideKernel<L, true, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a);
+        else twoPhaseCollideKernel<L, false, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a);
+    }
+    g_launches += 3;
+}
+} // namespace
+} // extern "C++"
+
+int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_steps)
+{
+    if (check(c, true)) return 1;
+    if (!p) return fail("params is null");
+    if (c->nFields != 2) return fail("chimp_step_twophase needs a two-field lattice");
+    if (c->lattice == CHIMP_D3Q27) return fail("D3Q27 has no colour-gradient weights B[] (not defined by the reference)");
+    if (!c->densitySet) return fail("call chimp_set_twophase_density first (wall colour, main_TWOPHASE.cpp:173-181)");
+    if (!c->nbrs.empty()) return fail("N-rank twophase stepping is not wired yet");
+    if (p->n_fluid_global <= 0) return fail("n_fluid_global must be positive");
+    CUDA_OK(cudaSetDevice(c->device));
+    TwoPhaseArgs a{};
+    a.stride = c->stride;
+    a.n = c->n;
+    a.nPad = c->nPad;
+    a.idx.table = c->d_table;
+    a.idx.delta = c->d_delta;
+    a.idx.base = c->d_base;
+    a.idx.rows = c->d_rows;
+    a.idx.nTiles = c->nTiles;
+    a.ptable = c->d_ptable;
+    a.phi = c->d_phi;
+    a.rho = c->d_rho;
+    a.vel = c->d_vel;
+    // main_TWOPHASE.cpp:126-129
+    a.nu0Inv = 1.0 / (kC2 * (p->tau0 - 0.5));
+    a.nu1Inv = 1.0 / (kC2 * (p->tau1 - 0.5));
+    a.sigma = p->sigma;
+    a.beta = p->beta;
+    for (int d = 0; d < 3; ++d) a.F[d] = d < c->li.nD ? p->force[d] : 0.0;
+    a.forceX = c->d_forceX;
+    a.partial = c->d_fluxPartial;
+    const unsigned gridAll = (unsigned)((c->n + 255) / 256);
+    for (int s = 0; s < n_steps; ++s) {
+        a.fin = c->d_f[c->cur];
+        a.fout = c->d_f[c->cur ^ 1];
+        a.begin = 0;
+        a.end = c->n;
+        const bool mom = (s == n_steps - 1);
+        if (c->lattice == CHIMP_D2Q9) launchTwoPhase<D2Q9>(c, a, p, mom, gridAll);
+        else launchTwoPhase<D3Q19>(c, a, p, mom, gridAll);
+        c->cur ^= 1;
+        ++c->steps;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int chimp_download_phase_field(chimp_lattice *c, double *cg)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2) return fail("needs a two-field lattice");
+    if (downloadPlanes(c, cg, c->d_phi, 1, 1, 0)) return 1;
+    // solid-boundary rows carry the constant wall colour (main_TWOPHASE.cpp:280-284)
+    std::vector<double> phiWall(std::max(c->nSolid, 1));
+    if (c->nSolid) CUDA_OK(cudaMemcpy(phiWall.data(), c->d_phi + c->nPad, (size_t)c->nSolid * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < c->nSolid; ++k) cg[c->solidBnd[k]] = phiWall[k];
+    return 0;
+}
+
+double chimp_last_flux_force(chimp_lattice *c)
+{
+    if (!c || !c->finalized || !c->d_forceX) return 0.0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    double v = 0.0;
+    cudaMemcpy(&v, c->d_forceX, sizeof(double), cudaMemcpyDeviceToHost);
+    return v;
+}
 
 // ---- halo plumbing ----------------------------------------------------------------------
 int chimp_num_neighbors(chimp_lattice *c) { return c ? (int)c->nbrs.size() : 0; }
@@ -1054,14 +1206,14 @@ int chimp_host_halo_lists(chimp_lattice *c, int k, long long *send_src, long lon
 }
 double chimp_irregular_fraction(chimp_lattice *c)
 {
-    if (!c || c->indexForm != CHIMP_INDEX_RANK || c->nTiles == 0) return 0.0;
+    if (!c || c->indexForm != CHIMP_INDEX_COMPACT || c->nTiles == 0) return 0.0;
     return (double)c->nRows / ((double)c->nTiles * c->li.nQ);
 }
 double chimp_index_bytes_per_node(chimp_lattice *c)
 {
     if (!c || c->n == 0) return 0.0;
     if (c->indexForm == CHIMP_INDEX_TABLE) return 4.0 * c->li.nQ;
-    return (4.0 * c->nPad + 4.0 * c->nTiles * c->li.nQ + 128.0 * c->nRows) / c->n;
+    return (4.0 * c->nWords * c->nPad + 4.0 * c->nTiles * c->li.nQ + 128.0 * c->nRows) / c->n;
 }
 long long chimp_plane_stride(chimp_lattice *c) { return c ? c->stride : 0; }
 

@@ -46,11 +46,31 @@ __global__ void massFinalizeKernel(const double *__restrict__ partial, int nBloc
     }
 }
 
-// ---- index compression (IDX_RANK) ------------------------------------------------------
-// One warp per (tile, q).  A pair is regular when every non-bounce lane l satisfies
-// T[q][32*tile + l] == base + (number of non-bounce lanes below l).
+// Folds the per-block x-momentum partials in a fixed order.  finish == 0: only the local sum is
+// written (an all-reduce over ranks follows); finish == 1: partial[] already holds the global
+// sum(s) and F_x = 2 (momx - sum / nGlobal) is produced (main_TWOPHASE.cpp:299-308).
+__global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks, double momx, double nGlobal,
+                                double *sumOut, double *forceX, int finish)
+{
+    __shared__ double sh[8];
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nBlocks; b += blockDim.x) v += partial[b];
+    const double s = blockSum256(v, sh);
+    if (threadIdx.x == 0) {
+        *sumOut = s;
+        if (finish) {
+            double mean = s;
+            mean /= nGlobal;
+            *forceX = 2 * (momx - mean);
+        }
+    }
+}
+
+// ---- index compression (IDX_COMPACT) ---------------------------------------------------
+// One warp per (tile, q): base = smallest non-bounce source of the tile; a pair whose
+// sources span more than 253 keeps an explicit row.
 __global__ void classifyTilesKernel(const int32_t *__restrict__ table, int n, int nPad, int nQ, int nTiles,
-                                    int32_t *__restrict__ base, uint32_t *__restrict__ bbmask, int *irregularCount)
+                                    int32_t *__restrict__ base, uint8_t *__restrict__ deltaBytes, int *irregularCount)
 {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
@@ -59,18 +79,18 @@ __global__ void classifyTilesKernel(const int32_t *__restrict__ table, int n, in
     const int i = tile * 32 + lane;
     const bool live = i < n;
     const int t = live ? table[(long long)q * nPad + i] : -1;
-    const bool bounce = (t == -1);
-    const unsigned bb = __ballot_sync(0xffffffffu, bounce);
-    const unsigned nb = ~bb;
-    int b0 = 0;
-    bool regular = true;
-    if (nb) {
-        const int first = __ffs(nb) - 1;
-        b0 = __shfl_sync(0xffffffffu, t, first);
-        const int expect = b0 + __popc(nb & ((1u << lane) - 1u));
-        regular = __all_sync(0xffffffffu, bounce || t == expect);
+    const bool bounce = (t < 0);
+    int mn = bounce ? 0x7fffffff : t, mx = bounce ? -1 : t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if (live && bounce) atomicOr(bbmask + i, 1u << q);
+    const bool any = mx >= 0;
+    const bool regular = !any || (mx - mn) <= 253;
+    const int b0 = any ? mn : 0;
+    // byte (q & 3) of word (q >> 2) of node i
+    deltaBytes[((long long)(q >> 2) * nPad + i) * 4 + (q & 3)] = (uint8_t)((bounce || !regular) ? 255 : (t - b0));
     if (lane == 0) {
         if (regular) base[(long long)q * nTiles + tile] = b0;
         else base[(long long)q * nTiles + tile] = -(atomicAdd(irregularCount, 1) + 1);
@@ -87,8 +107,7 @@ __global__ void fillRowsKernel(const int32_t *__restrict__ table, int n, int nPa
     const int b = base[(long long)q * nTiles + tile];
     if (b >= 0) return;
     const int i = tile * 32 + lane;
-    const int t = (i < n) ? table[(long long)q * nPad + i] : 0;
-    rows[((long long)(-b - 1) << 5) + lane] = t < 0 ? 0 : t;
+    rows[((long long)(-b - 1) << 5) + lane] = (i < n) ? table[(long long)q * nPad + i] : -1;
 }
 
 } // namespace chimp

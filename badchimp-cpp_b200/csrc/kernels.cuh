@@ -14,9 +14,11 @@
 // state through T (gather), collides, and writes the node's own slots of the other buffer
 // (fully coalesced).  Two buffers (A/B) alternate.
 //
-// Index forms: IDX_TABLE reads the int32 table T[q][n]; IDX_RANK is the compressed form
-// (per-node bounce-back bitmask + one base per (32-node tile, q); source of lane l is
-// base + popc(non-bounce lanes below l); irregular (tile,q) pairs fall back to explicit rows).
+// Index forms: IDX_TABLE reads the int32 table T[q][n]; IDX_COMPACT is the compressed form:
+// one int32 base per (32-node tile, q) plus one byte per (node, q), packed four directions to
+// a 32-bit word: source = base + byte, byte 255 = reversed own slot (bounce back).  vtklb
+// numbers fluid nodes consecutively along z, so the sources of a tile span a short label
+// range; the few (tile, q) pairs whose span exceeds 253 fall back to explicit 32-entry rows.
 #pragma once
 #include <cstdint>
 #include <utility>
@@ -24,14 +26,22 @@
 
 namespace chimp {
 
+// launch shape of the collide-stream kernels (tuned on B200)
+#ifndef CHIMP_BLOCK
+#define CHIMP_BLOCK 256
+#endif
+#ifndef CHIMP_MIN_BLOCKS
+#define CHIMP_MIN_BLOCKS 3
+#endif
+
 enum { COLL_BGK = 0, COLL_TRT = 1 };
-enum { IDX_TABLE = 0, IDX_RANK = 1 };
+enum { IDX_TABLE = 0, IDX_COMPACT = 1 };
 
 struct IndexView {
     const int32_t *table;    // IDX_TABLE: [nQ][nPad]
-    const uint32_t *bbmask;  // IDX_RANK : [nPad] bit q set -> f_q(n) = X[rev q][n]; bit 31: node is real
-    const int32_t *base;     // IDX_RANK : [nQ][nTiles]; >= 0 regular base, < 0: -(row+1) into `rows`
-    const int32_t *rows;     // IDX_RANK : explicit rows [nRows][32]
+    const uint32_t *delta;   // IDX_COMPACT : [nWords][nPad], byte (q & 3) of word (q >> 2): source - base, 255 = bounce
+    const int32_t *base;     // IDX_COMPACT : [nQ][nTiles]; >= 0 smallest source of the tile, < 0: -(row+1) into `rows`
+    const int32_t *rows;     // IDX_COMPACT : explicit rows [nRows][32] (-1 = bounce)
     int nTiles;
 };
 
@@ -59,6 +69,13 @@ struct StepArgs {
     double *vel; // [nD][nPad]
 };
 
+// runtime-q weight lookup for the rare boundary branch (folds when q is a constant)
+template <class L>
+__device__ __forceinline__ double chimp_w(int q)
+{
+    return L::w(q);
+}
+
 template <class F, int... Q>
 __device__ __forceinline__ void staticForImpl(F &f, std::integer_sequence<int, Q...>)
 {
@@ -71,46 +88,59 @@ __device__ __forceinline__ void staticFor(F &f)
     staticForImpl(f, std::make_integer_sequence<int, N>{});
 }
 
+// Resolves, for node i and every direction q, where f_q(i) lives in one field's planes
+// (offset in doubles from the field base) and hands it to fn(q, offset).  `a` is any argument
+// block with stride / nPad / idx members.  All 32 lanes of a warp must call this together in
+// IDX_COMPACT form; dead lanes pass live = false and get offset 0.
+template <class L, int IDX, class Args, class Fn>
+__device__ __forceinline__ void forEachSource(const Args &a, int i, bool live, Fn &&fn)
+{
+    if (IDX == IDX_TABLE) {
+        int src[L::nQ];
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) src[q] = live ? __ldg(a.idx.table + (long long)q * a.nPad + i) : 0;
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) {
+            const int s = src[q];
+            const long long off = (s >= 0) ? (long long)q * a.stride + s : (long long)reverseDir<L>(q) * a.stride + i;
+            fn(q, live ? off : 0ll);
+        }
+    } else {
+        constexpr int NW = (L::nQ + 3) / 4;
+        const int tile = i >> 5;
+        const unsigned lane = threadIdx.x & 31u;
+        // every index word of the node / tile is requested before anything waits on one
+        uint32_t wd[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) wd[w] = live ? __ldg(a.idx.delta + (long long)w * a.nPad + i) : 0xffffffffu;
+        int base[L::nQ];
+        const int tl = min(tile, a.idx.nTiles - 1);
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) base[q] = __ldg(a.idx.base + (long long)q * a.idx.nTiles + tl);
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) {
+            const int b = base[q];
+            const int d = (int)((wd[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            int s = b + d;
+            bool bounce = d == 255;
+            if (b < 0) { // warp-uniform: this (tile, q) keeps an explicit row
+                s = live ? __ldg(a.idx.rows + ((long long)(-b - 1) << 5) + lane) : 0;
+                bounce = s < 0;
+            }
+            const long long off = bounce ? (long long)reverseDir<L>(q) * a.stride + i : (long long)q * a.stride + s;
+            fn(q, live ? off : 0ll);
+        }
+    }
+}
+
 template <class L, int IDX>
 struct Gather {
-    // loads f_q(n) for all q of node i (lane = i & 31)
-    __device__ __forceinline__ static void load(const StepArgs &a, const double *__restrict__ fin, int i, bool live,
+    // loads f_q(n) for all q of node i (lane = i & 31) from the field starting at fin
+    template <class Args>
+    __device__ __forceinline__ static void load(const Args &a, const double *__restrict__ fin, int i, bool live,
                                                 double (&f)[L::nQ])
     {
-        if (IDX == IDX_TABLE) {
-            if (!live) {
-#pragma unroll
-                for (int q = 0; q < L::nQ; ++q) f[q] = 0.0;
-                return;
-            }
-            int src[L::nQ];
-#pragma unroll
-            for (int q = 0; q < L::nQ; ++q) src[q] = __ldg(a.idx.table + (long long)q * a.nPad + i);
-#pragma unroll
-            for (int q = 0; q < L::nQ; ++q) {
-                const int s = src[q];
-                const double *p = (s >= 0) ? fin + (long long)q * a.stride + s
-                                           : fin + (long long)reverseDir<L>(q) * a.stride + i;
-                f[q] = __ldg(p);
-            }
-        } else {
-            const uint32_t m = live ? __ldg(a.idx.bbmask + i) : 0xffffffffu;
-            const int tile = i >> 5;
-            const unsigned lane = threadIdx.x & 31u;
-            const unsigned below = (1u << lane) - 1u;
-#pragma unroll
-            for (int q = 0; q < L::nQ; ++q) {
-                const int b = tile < a.idx.nTiles ? __ldg(a.idx.base + (long long)q * a.idx.nTiles + tile) : 0;
-                const unsigned bb = __ballot_sync(0xffffffffu, (m >> q) & 1u);
-                int s;
-                if (b >= 0) s = b + __popc(~bb & below);
-                else s = __ldg(a.idx.rows + ((long long)(-b - 1) << 5) + lane);
-                const bool bounce = (m >> q) & 1u;
-                const double *p = bounce ? fin + (long long)reverseDir<L>(q) * a.stride + i
-                                         : fin + (long long)q * a.stride + s;
-                f[q] = live ? __ldg(p) : 0.0;
-            }
-        }
+        forEachSource<L, IDX>(a, i, live, [&](int q, long long off) { f[q] = live ? __ldg(fin + off) : 0.0; });
     }
 };
 
@@ -120,12 +150,12 @@ struct Gather {
 // Reference loop bodies: std_case/main.cpp:110-135, std_one_phase/main.cpp:534-575.
 // ---------------------------------------------------------------------------------------
 template <class L, int COLL, bool ONEPHASE, bool MOM, int IDX>
-__global__ void __launch_bounds__(256) collideStreamKernel(const StepArgs a)
+__global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKernel(const StepArgs a)
 {
     const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.end;
     if (IDX == IDX_TABLE && !live) return;
-    if (IDX == IDX_RANK && (i & ~31) >= a.end) return; // whole warp out of range
+    if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return; // whole warp out of range
 
     double f[L::nQ];
     Gather<L, IDX>::load(a, a.fin, i, live, f);
@@ -156,38 +186,85 @@ __global__ void __launch_bounds__(256) collideStreamKernel(const StepArgs a)
     const double uF = dotD<L>(u, F);
     uint32_t pm = 0;
     if (ONEPHASE && a.pmask) pm = a.pmask[i];
+    double *const fout = a.fout + i;
 
-    double out[L::nQ];
-    // compile-time q via recursive lambda-free unrolling
-    auto body = [&](auto qc) {
-        constexpr int q = decltype(qc)::value;
+    // Opposite directions are collided together.  With c_r = -c_q every intermediate of the
+    // reversed direction is the exact IEEE negation (c.u, c.F, 3 c.u, 3 c.F, the TRT odd part) or
+    // the identical value ((c.u)^2, (c.F)(c.u)) of the forward one, so sharing them reproduces the
+    // reference's per-direction arithmetic (LBcollision.h:43,67-72,95,118,210,233) bit for bit
+    // with a third fewer FP64 instructions.
+    const double c2u2 = kC2 * u2, c2uF = kC2 * uF;
+    const double negTauInv = -a.tauInv, negSymInv = -a.tauSymInv;
+    auto finish = [&](int q, double v, double cu) {
+        if (ONEPHASE && ((pm >> q) & 1u)) {
+            // anti bounce back (std_one_phase/main.cpp:168-172): this slot is only pulled back by
+            // the node's own reversed direction, so it can carry the boundary value directly
+            v = -v + 2 * chimp_w<L>(q) * a.rhoW * (1 + 0.5 * (kC4Inv * cu * cu - kC2Inv * u2));
+        }
+        fout[(long long)q * a.stride] = v;
+    };
+    auto pairBody = [&](auto pc) {
+        constexpr int q = decltype(pc)::value, r = q + L::nPairs;
         const double cu = cDot<L, q>(u);
         const double cF = cDot<L, q>(F);
+        const double t = kC4Inv0_5 * (cu * cu - c2u2);
+        const double m3 = kC2Inv * cu;
+        const double rw = rho * L::w(q);
+        const double g = kC4Inv * (cF * cu - c2uF);
+        const double h = kC2Inv * cF;
+        double vq, vr;
+        if (COLL == COLL_BGK) {
+            const double eq = 1.0 + m3 + t, er = 1.0 - m3 + t;
+            const double wtf = L::w(q) * a.tauFactor;
+            vq = f[q] + negTauInv * (f[q] - rw * eq) + wtf * (h + g);
+            vr = f[r] + negTauInv * (f[r] - rw * er) + wtf * (g - h);
+            if (ONEPHASE) {
+                const double tsw = a.tauFactor * qSrc * L::w(q);
+                vq = vq + tsw * eq;
+                vr = vr + tsw * er;
+            }
+        } else {
+            const double fSym = 0.5 * (f[q] + f[r]);
+            const double fAnti = 0.5 * (f[q] - f[r]);
+            const double es = 1.0 + t;
+            const double S = negSymInv * (fSym - rw * es);
+            const double A = a.tauAntiInv * (fAnti - rw * kC2Inv * cu);
+            const double w1 = L::w(q) * 1.0; // phi = 1.0 (call pattern of rans/main.cpp:530)
+            const double ah = a.antiFactor * kC2Inv * cF;
+            const double sg = a.symFactor * kC4Inv * (cF * cu - c2uF);
+            vq = f[q] + (S - A) + w1 * (ah + sg);
+            vr = f[r] + (S + A) + w1 * (sg - ah);
+            if (ONEPHASE) {
+                const double sw = qSrc * L::w(q);
+                const double am = a.antiFactor * kC2Inv * cu;
+                const double se = a.symFactor * es;
+                vq = vq + sw * (am + se);
+                vr = vr + sw * (se - am);
+            }
+        }
+        finish(q, vq, cu);
+        finish(r, vr, cu);
+    };
+    staticFor<L::nPairs>(pairBody);
+    {
+        // rest direction: c = 0
+        constexpr int q = L::nQ - 1;
         double om, dF;
         if (COLL == COLL_BGK) {
-            om = omegaBGK<L, q>(f[q], a.tauInv, rho, cu, u2);
-            dF = deltaOmegaF<L, q>(a.tauFactor, cu, uF, cF);
+            om = omegaBGK<L, q>(f[q], a.tauInv, rho, 0.0, u2);
+            dF = deltaOmegaF<L, q>(a.tauFactor, 0.0, uF, 0.0);
         } else {
-            om = omegaTRT<L, q>(f[q], f[reverseDir<L>(q)], a.tauSymInv, a.tauAntiInv, rho, cu, u2);
-            dF = deltaOmegaFTRT<L, q>(a.symFactor, a.antiFactor, 1.0, cu, uF, cF);
+            om = omegaTRT<L, q>(f[q], f[q], a.tauSymInv, a.tauAntiInv, rho, 0.0, u2);
+            dF = deltaOmegaFTRT<L, q>(a.symFactor, a.antiFactor, 1.0, 0.0, uF, 0.0);
         }
         double v = f[q] + om + dF;
         if (ONEPHASE) {
-            const double dQ = (COLL == COLL_BGK) ? deltaOmegaQ<L, q>(a.tauFactor, cu, u2, qSrc)
-                                                 : deltaOmegaQTRT<L, q>(a.symFactor, a.antiFactor, cu, u2, qSrc);
+            const double dQ = (COLL == COLL_BGK) ? deltaOmegaQ<L, q>(a.tauFactor, 0.0, u2, qSrc)
+                                                 : deltaOmegaQTRT<L, q>(a.symFactor, a.antiFactor, 0.0, u2, qSrc);
             v = v + dQ;
-            if ((pm >> q) & 1u) {
-                // anti bounce back: the slot is only ever pulled back by this node's reverse
-                // direction (std_one_phase/main.cpp:168-172, w and cu of the known direction q)
-                v = -v + 2 * L::w(q) * a.rhoW * (1 + 0.5 * (kC4Inv * cu * cu - kC2Inv * u2));
-            }
         }
-        out[q] = v;
-    };
-    staticFor<L::nQ>(body);
-
-#pragma unroll
-    for (int q = 0; q < L::nQ; ++q) a.fout[(long long)q * a.stride + i] = out[q];
+        finish(q, v, 0.0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -231,6 +308,128 @@ __global__ void __launch_bounds__(256) massChangeKernel(const StepArgs a, int nL
 // one block per label: mass[l] = sum of partials; src[l] = 0.9*2*scale[l]*mass[l] (main.cpp:548)
 __global__ void massFinalizeKernel(const double *__restrict__ partial, int nBlocks, const double *__restrict__ scale,
                                    double *mass, double *src);
+
+// ---------------------------------------------------------------------------------------
+// Colour-gradient two-phase path (twophase/main_TWOPHASE.cpp:236-392), two LbFields.
+//   phaseMomentsKernel : pass A (:238-246) rho0, rho1, phi for own nodes, and the per-block
+//                        partial sums of the x-momentum of pass C (:292-299)
+//   fluxForceKernel    : folds the partials (fixed order) -> F_x = 2 (momx - mean) (:301-308)
+//   twoPhaseCollideKernel : pass D (:312-376) collide + recolour + stream of both fields
+// phi lives in an array of "phi slots": own nodes first, then solid-boundary nodes (constant
+// wettability value, :280-284), ghost nodes (filled by the scalar halo exchange, :287) and one
+// zero slot for every other neighbour (cgField is zero-initialised there).
+// ---------------------------------------------------------------------------------------
+struct TwoPhaseArgs {
+    const double *fin;
+    double *fout;
+    long long stride;
+    int n, nPad, begin, end;
+    IndexView idx;
+    const int32_t *ptable; // [nQ][nPad] phi slot of neighbor(q, n)  (LButilities.h:12-22)
+    double *phi;
+    double *rho; // [2][nPad]
+    double *vel; // [nD][nPad]
+    double nu0Inv, nu1Inv, sigma, beta;
+    double F[3];
+    const double *forceX; // device scalar written by fluxForceKernel
+    double *partial;
+};
+
+template <class L, int IDX>
+__global__ void __launch_bounds__(256) phaseMomentsKernel(const TwoPhaseArgs a)
+{
+    __shared__ double sh[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    double f0[L::nQ], f1[L::nQ];
+    const double *fin1 = a.fin + (long long)L::nQ * a.stride;
+    forEachSource<L, IDX>(a, live ? i : 0, live, [&](int q, long long off) {
+        f0[q] = live ? __ldg(a.fin + off) : 0.0;
+        f1[q] = live ? __ldg(fin1 + off) : 0.0;
+    });
+    double mom = 0.0;
+    if (live) {
+        const double r0 = nodeRho<L>(f0), r1 = nodeRho<L>(f1);
+        a.rho[i] = r0;
+        a.rho[(long long)a.nPad + i] = r1;
+        a.phi[i] = (r0 - r1) / (r0 + r1);
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) f0[q] = f0[q] + f1[q];
+        mom = firstMoment<L, 0>(f0);
+    }
+    const double s = blockSum256(mom, sh);
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = s;
+}
+
+__global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks, double momx, double nGlobal,
+                                double *sumOut, double *forceX, int finish);
+
+template <class L, bool MOM, int IDX>
+__global__ void __launch_bounds__(256) twoPhaseCollideKernel(const TwoPhaseArgs a)
+{
+    const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.end;
+    if (IDX == IDX_TABLE && !live) return;
+    if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return;
+    double fTot[L::nQ];
+    const double *fin1 = a.fin + (long long)L::nQ * a.stride;
+    forEachSource<L, IDX>(a, i, live, [&](int q, long long off) {
+        fTot[q] = live ? __ldg(a.fin + off) + __ldg(fin1 + off) : 0.0;
+    });
+    if (!live) return;
+    const double rho0 = a.rho[i], rho1 = a.rho[(long long)a.nPad + i];
+    const double rho = rho0 + rho1;
+    double F[3] = {*a.forceX, a.F[1], a.F[2]};
+    double u[3] = {0.0, 0.0, 0.0};
+    u[0] = (firstMoment<L, 0>(fTot) + 0.5 * F[0]) / rho;
+    u[1] = (firstMoment<L, 1>(fTot) + 0.5 * F[1]) / rho;
+    if (L::nD == 3) u[2] = (firstMoment<L, 2>(fTot) + 0.5 * F[2]) / rho;
+    if (MOM) {
+#pragma unroll
+        for (int d = 0; d < L::nD; ++d) a.vel[(long long)d * a.nPad + i] = u[d];
+    }
+    // main_TWOPHASE.cpp:340
+    const double tau = kC2Inv * rho / (rho0 * a.nu0Inv + rho1 * a.nu1Inv) + 0.5;
+    const double tauInv = 1.0 / tau, tauFactor = (1 - 0.5 / tau);
+    const double uu = dotD<L>(u, u);
+    const double uF = dotD<L>(u, F);
+    // colour gradient (LButilities.h:12-22 -> LBd3q19.h:155-163)
+    double ph[L::nQ];
+#pragma unroll
+    for (int q = 0; q < L::nQ; ++q) ph[q] = a.phi[__ldg(a.ptable + (long long)q * a.nPad + i)];
+    double g[3] = {0.0, 0.0, 0.0};
+    g[0] = latticeGrad<L, 0>(ph);
+    g[1] = latticeGrad<L, 1>(ph);
+    if (L::nD == 3) g[2] = latticeGrad<L, 2>(ph);
+    const double CGNorm = sqrt(dotD<L>(g, g));
+    const double inv = 1.0 / (CGNorm + (CGNorm < 2.220446049250313e-16 ? 1.0 : 0.0)); // lbBaseEps (LBglobal.h:14)
+#pragma unroll
+    for (int d = 0; d < L::nD; ++d) g[d] *= inv;
+    const double AF0_5 = 1.125 * CGNorm * a.sigma / tau;      // LBcollision2phase.h:12
+    const double rhoFacBeta = a.beta * rho0 * rho1 / rho;     // LBcollision2phase.h:74
+    const double c0 = (rho0 / rho), c1 = (rho1 / rho);
+    double *fout1 = a.fout + (long long)L::nQ * a.stride;
+    auto body = [&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const double cu = cDot<L, q>(u);
+        const double cF = cDot<L, q>(F);
+        const double om = omegaBGK<L, q>(fTot[q], tauInv, rho, cu, uu);
+        const double dF = deltaOmegaF<L, q>(tauFactor, cu, uF, cF);
+        double st, rc;
+        if (q < L::nQ - 1) {
+            const double cCG = cDot<L, q>(g);
+            st = AF0_5 * (L::w(q) * cCG * cCG - L::B(q));
+            rc = rhoFacBeta * L::w(q) * cCG / cNorm<L, q>();
+        } else {
+            st = -AF0_5 * L::B(q);
+            rc = 0.0;
+        }
+        const double common = fTot[q] + om + dF + st;
+        a.fout[(long long)q * a.stride + i] = c0 * common + rc;
+        fout1[(long long)q * a.stride + i] = c1 * common - rc;
+    };
+    staticFor<L::nQ>(body);
+}
 
 // ---------------------------------------------------------------------------------------
 // Layout conversion between the reference AoS field (LBfield.h:300:

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size", type=int, default=0, help="edge length of the cubic sphere pack (0 = default)")
-    ap.add_argument("--index", default="rank", choices=["rank", "table"])
+    ap.add_argument("--index", default="compact", choices=["compact", "table"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     import helpers

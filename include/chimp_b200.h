@@ -26,7 +26,7 @@ enum { CHIMP_D2Q9 = 0, CHIMP_D3Q19 = 1, CHIMP_D3Q27 = 2 };
 /* collision operators: calcOmegaBGK (LBcollision.h:27), calcOmegaBGKTRT (LBcollision.h:50) */
 enum { CHIMP_BGK = 0, CHIMP_TRT = 1 };
 /* index forms of the streaming step */
-enum { CHIMP_INDEX_TABLE = 0, CHIMP_INDEX_RANK = 1 };
+enum { CHIMP_INDEX_TABLE = 0, CHIMP_INDEX_COMPACT = 1 };
 /* link boundary kinds of std_one_phase/main.cpp:138-203 */
 enum { CHIMP_LINK_SOLID = 0, CHIMP_LINK_PRESSURE = 1, CHIMP_LINK_FLUID_SWAP = 2 };
 
@@ -78,7 +78,7 @@ int chimp_host_table_info(chimp_lattice *, long long *info6);
 int chimp_host_table(chimp_lattice *, int32_t *table, int32_t *labels, uint32_t *pmask);
 int chimp_host_halo_lists(chimp_lattice *, int k, long long *send_src, long long *recv_dst);
 
-/* builds the device tables; index_form is CHIMP_INDEX_TABLE or CHIMP_INDEX_RANK.
+/* builds the device tables; index_form is CHIMP_INDEX_TABLE or CHIMP_INDEX_COMPACT.
  * boundary_first != 0 orders halo-coupled nodes first so that their step can overlap. */
 int chimp_finalize(chimp_lattice *, int index_form, int boundary_first);
 
@@ -164,7 +164,7 @@ int chimp_synchronize(chimp_lattice *);
 
 /* ---- introspection for tests / bench */
 int chimp_num_own_nodes(chimp_lattice *);
-/* fraction of (tile, q) pairs that needed explicit rows in CHIMP_INDEX_RANK form */
+/* fraction of (tile, q) pairs that needed explicit rows in CHIMP_INDEX_COMPACT form */
 double chimp_irregular_fraction(chimp_lattice *);
 /* device bytes of index data read per node per step, and of population data */
 double chimp_index_bytes_per_node(chimp_lattice *);

@@ -199,3 +199,47 @@ def test_round_trip_upload_download():
     out = lat.download()
     bulk = tabs[0].bulk_nodes()
     assert np.array_equal(out[bulk], f[bulk])
+
+
+@pytest.mark.parametrize("index_form", [0, 1])
+@pytest.mark.parametrize("name", ["twophase_d3q19_p1", "twophase_d2q9_p1"])
+def test_twophase_vs_reference(name, index_form):
+    """colour-gradient two-phase loop (2 LbFields).  The flux-control force comes from a global
+    x-momentum sum that is a tree sum on the GPU (sequential on the CPU): F_x agrees to ~1e-13
+    relative and enters f scaled by ~1e-6, so populations are compared at 1e-12 relative
+    (north_star's per-step bar); rho0, rho1, phi of the step are computed before the force and
+    are bit-exact on the first step."""
+    g = helpers.Golden(name)
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    t = tabs[0]
+    setup = pkg.cases.two_phase_setup(lg, tabs, g.attr("rho0"), g.attr("rho1"), g.attr("wettability"))[0]
+    lat = pkg.capi.Lattice.from_rank_tables(t, n_fields=2)
+    lat.add_halfway_bb(*t.halfway_bb(t.bulk_nodes()))
+    lat.set_solid_boundary(setup["solid_bnd"])
+    lat.finalize(index_form)
+    lat.set_twophase_density(setup["rho"])
+    lat.upload(setup["f0"])
+    a = g.args
+    bulk = t.bulk_nodes()
+    done = 0
+    for step in [s for s in g.dump if s > 0]:
+        lat.step_twophase(step - done, a["tau2"][0], a["tau2"][1], a["sigma"], a["beta"], a["momx"], g.force(), len(bulk))
+        done = step
+        ref_f = g.f(0, step, 2)[bulk]
+        got = lat.download()[bulk]
+        assert np.allclose(got, ref_f, rtol=1e-12, atol=1e-300)
+        ref_rho = g.rec(0, "step%d.rho" % step).reshape(-1, 2)[bulk]
+        got_rho = lat.download_rho()[bulk]
+        assert np.allclose(got_rho, ref_rho, rtol=1e-12, atol=0)
+        ref_cg = g.rec(0, "step%d.cg" % step)
+        got_cg = lat.download_phase_field()
+        assert np.allclose(got_cg[bulk], ref_cg[bulk], rtol=1e-10, atol=1e-14)
+        sb = setup["solid_bnd"]
+        assert np.array_equal(got_cg[sb], ref_cg[sb])
+        assert np.allclose(lat.download_vel()[bulk], g.rec(0, "step%d.vel" % step).reshape(t.size, -1)[bulk],
+                           rtol=1e-9, atol=1e-16)
+        fx = float(g.rec(0, "step%d.forceX" % step)[0])
+        assert abs(lat.last_flux_force() - fx) <= 1e-10 * abs(fx)
+        if step == 1:
+            assert np.array_equal(got_rho, ref_rho)
