@@ -52,7 +52,7 @@ SYMBOLS = [
     "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_irregular_fraction",
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
-    "chimp_set_halo_buffers", "chimp_halo_stream",
+    "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count",
 ]
 
 
@@ -266,6 +266,15 @@ class Lattice:
 
     def set_halo_buffers(self, k, send_ptr, recv_ptr):
         _check(lib().chimp_set_halo_buffers(self.h, C.c_int(k), C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))
+
+    def add_halo_face(self, rank, send_src, recv_dst):
+        send_src = np.ascontiguousarray(send_src, dtype=np.int64)
+        recv_dst = np.ascontiguousarray(recv_dst, dtype=np.int64)
+        _check(lib().chimp_add_halo_face(self.h, C.c_int(rank), C.c_longlong(len(send_src)), _p(send_src),
+                                         C.c_longlong(len(recv_dst)), _p(recv_dst)))
+
+    def set_boundary_count(self, n):
+        _check(lib().chimp_set_boundary_count(self.h, C.c_int(n)))
 
     def halo_stream(self):
         return lib().chimp_halo_stream(self.h)

@@ -27,7 +27,8 @@ __global__ void fluxForceKernel(const double *, int, double, double, double *, d
 __global__ void massFinalizeKernel(const double *, int, const double *, double *, double *);
 __global__ void fillKernel(double *p, double v, long long count);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
-__global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *);
+__global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *, int, long long);
+__global__ void kernelTableKernel(const int32_t *, int32_t *, int, int, int, int, long long);
 } // namespace chimp
 
 using namespace chimp;
@@ -108,7 +109,7 @@ struct chimp_lattice {
     int n = 0, nPad = 0, nHalo = 0, nBoundary = 0;
     long long stride = 0;
     int indexForm = CHIMP_INDEX_TABLE;
-    int32_t *d_table = nullptr, *d_label = nullptr;
+    int32_t *d_table = nullptr, *d_ktable = nullptr, *d_label = nullptr;
     uint32_t *d_delta = nullptr, *d_pmask = nullptr;
     int nWords = 0;
     int32_t *d_base = nullptr, *d_rows = nullptr;
@@ -164,6 +165,24 @@ int allocateState(chimp_lattice *c)
     return 0;
 }
 
+int buildKernelTable(chimp_lattice *c)
+{
+    const long long total = (long long)c->li.nQ * c->nPad;
+    CUDA_OK(cudaMalloc(&c->d_ktable, (size_t)total * sizeof(int32_t)));
+    kernelTableKernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_table, c->d_ktable, c->n, c->nPad, c->li.nQ, c->li.nPairs, c->stride);
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int checkIndexRange(chimp_lattice *c)
+{
+    // slot indices are signed 32-bit relative to a plane, bounces reach nPairs planes away
+    if ((long long)c->li.nPairs * c->stride + c->nPad >= (1ll << 31))
+        return fail("lattice too large for 32-bit plane-relative indices (%lld slots per plane)", c->stride);
+    return 0;
+}
+
 int buildRankIndex(chimp_lattice *c)
 {
     const int nQ = c->li.nQ;
@@ -171,7 +190,8 @@ int buildRankIndex(chimp_lattice *c)
     c->nWords = (nQ + 3) / 4;
     CUDA_OK(cudaMalloc(&c->d_delta, (size_t)c->nWords * c->nPad * sizeof(uint32_t)));
     CUDA_OK(cudaMemsetAsync(c->d_delta, 0xff, (size_t)c->nWords * c->nPad * sizeof(uint32_t), c->stream));
-    CUDA_OK(cudaMalloc(&c->d_base, (size_t)c->nTiles * nQ * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&c->d_base, (size_t)c->nTiles * c->nWords * 4 * sizeof(int32_t)));
+    CUDA_OK(cudaMemsetAsync(c->d_base, 0, (size_t)c->nTiles * c->nWords * 4 * sizeof(int32_t), c->stream));
     int *d_cnt = nullptr;
     CUDA_OK(cudaMalloc(&d_cnt, sizeof(int)));
     CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(int), c->stream));
@@ -187,7 +207,7 @@ int buildRankIndex(chimp_lattice *c)
     c->nRows = cnt;
     CUDA_OK(cudaMalloc(&c->d_rows, (size_t)std::max(cnt, 1) * 32 * sizeof(int32_t)));
     if (cnt > 0) {
-        fillRowsKernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->n, c->nPad, nQ, c->nTiles, c->d_base, c->d_rows);
+        fillRowsKernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->n, c->nPad, nQ, c->nTiles, c->d_base, c->d_rows, c->li.nPairs, c->stride);
         ++g_launches;
         CUDA_OK(cudaGetLastError());
     }
@@ -641,7 +661,9 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
         CUDA_OK(cudaMemset(c->d_forceX, 0, sizeof(double)));
     }
     c->indexForm = index_form;
+    if (checkIndexRange(c)) return 1;
     if (index_form == CHIMP_INDEX_COMPACT && buildRankIndex(c)) return 1;
+    if (index_form == CHIMP_INDEX_TABLE && buildKernelTable(c)) return 1;
     if (allocateState(c)) return 1;
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->finalized = true;
@@ -681,7 +703,9 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
     CUDA_OK(cudaMemcpyAsync(c->d_label, label_dev, (size_t)n_pad * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
     c->hostBuilt = true;
     c->indexForm = index_form;
+    if (checkIndexRange(c)) { chimp_destroy(c); return 1; }
     if (index_form == CHIMP_INDEX_COMPACT && buildRankIndex(c)) { chimp_destroy(c); return 1; }
+    if (index_form == CHIMP_INDEX_TABLE && buildKernelTable(c)) { chimp_destroy(c); return 1; }
     if (allocateState(c)) { chimp_destroy(c); return 1; }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->finalized = true;
@@ -694,7 +718,7 @@ void chimp_destroy(chimp_lattice *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    freeDev(c->d_table); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
+    freeDev(c->d_table); freeDev(c->d_ktable); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
     freeDev(c->d_rho); freeDev(c->d_vel);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
@@ -848,6 +872,26 @@ int chimp_set_one_phase_attributes(chimp_lattice *c, const double *force_on, con
 // ---- stepping -----------------------------------------------------------------------------
 namespace {
 
+void fillIndexView(const chimp_lattice *c, IndexView &v)
+{
+    v.table = c->d_ktable;
+    v.delta = c->d_delta;
+    v.base = c->d_base;
+    v.rows = c->d_rows;
+    v.nTiles = c->nTiles;
+    for (int q = 0; q < c->li.nQ; ++q) v.bounceOff[q] = (int)((long long)(revDir(c->li, q) - q) * c->stride);
+}
+
+void fillPlanes(const chimp_lattice *c, Planes &pl)
+{
+    const double *in = c->d_f[c->cur];
+    double *out = c->d_f[c->cur ^ 1];
+    for (int q = 0; q < c->li.nQ; ++q) {
+        pl.in[q] = in + (long long)q * c->stride;
+        pl.out[q] = out + (long long)q * c->stride;
+    }
+}
+
 int fillStepArgs(chimp_lattice *c, const chimp_single_params *p, StepArgs &a)
 {
     if (!p) return fail("params is null");
@@ -858,11 +902,7 @@ int fillStepArgs(chimp_lattice *c, const chimp_single_params *p, StepArgs &a)
     a.stride = c->stride;
     a.n = c->n;
     a.nPad = c->nPad;
-    a.idx.table = c->d_table;
-    a.idx.delta = c->d_delta;
-    a.idx.base = c->d_base;
-    a.idx.rows = c->d_rows;
-    a.idx.nTiles = c->nTiles;
+    fillIndexView(c, a.idx);
     // LBcollision.h:39,65-66,91,113-114,206,228-229: per-call constants of the reference helpers
     a.tauInv = 1.0 / p->tau;
     a.tauFactor = (1 - 0.5 / p->tau);
@@ -890,8 +930,8 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom)
 {
     StepArgs a;
     if (fillStepArgs(c, p, a)) return 1;
-    a.fin = c->d_f[c->cur];
-    a.fout = c->d_f[c->cur ^ 1];
+    fillPlanes(c, a.pl);
+    double *const foutBuf = c->d_f[c->cur ^ 1];
     if (c->onePhase && c->nLabels > 1 && massChangePass(c, a)) return 1;
     if (c->nbrs.empty()) {
         a.begin = 0;
@@ -904,7 +944,7 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom)
     dispatchSingleLattice(c, a, p->collision, mom, c->stream);
     for (auto &nb : c->nbrs)
         if (nb.sendCount) {
-            haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.sendBuf(), a.fout, nb.d_sendSrc, (int)nb.sendCount);
+            haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.sendBuf(), foutBuf, nb.d_sendSrc, (int)nb.sendCount);
             ++g_launches;
         }
     CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
@@ -1080,11 +1120,7 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     a.stride = c->stride;
     a.n = c->n;
     a.nPad = c->nPad;
-    a.idx.table = c->d_table;
-    a.idx.delta = c->d_delta;
-    a.idx.base = c->d_base;
-    a.idx.rows = c->d_rows;
-    a.idx.nTiles = c->nTiles;
+    fillIndexView(c, a.idx);
     a.ptable = c->d_ptable;
     a.phi = c->d_phi;
     a.rho = c->d_rho;
@@ -1099,8 +1135,7 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     a.partial = c->d_fluxPartial;
     const unsigned gridAll = (unsigned)((c->n + 255) / 256);
     for (int s = 0; s < n_steps; ++s) {
-        a.fin = c->d_f[c->cur];
-        a.fout = c->d_f[c->cur ^ 1];
+        fillPlanes(c, a.pl);
         a.begin = 0;
         a.end = c->n;
         const bool mom = (s == n_steps - 1);
@@ -1155,6 +1190,43 @@ int chimp_set_halo_buffers(chimp_lattice *c, int k, void *send_dev, void *recv_d
     return 0;
 }
 void *chimp_halo_stream(chimp_lattice *c) { return c ? (void *)c->haloStream : nullptr; }
+
+int chimp_add_halo_face(chimp_lattice *c, int neig_rank, long long n_send, const long long *send_src, long long n_recv,
+                        const long long *recv_dst)
+{
+    if (check(c, true)) return 1;
+    if (n_send < 0 || n_recv < 0 || n_send >= (1ll << 31) || n_recv >= (1ll << 31)) return fail("bad halo face size");
+    CUDA_OK(cudaSetDevice(c->device));
+    const long long planeSlots = c->stride * c->li.nQ;
+    for (long long k = 0; k < n_send; ++k)
+        if (send_src[k] < 0 || send_src[k] >= planeSlots) return fail("send offset %lld out of range", send_src[k]);
+    for (long long k = 0; k < n_recv; ++k)
+        if (recv_dst[k] < 0 || recv_dst[k] >= planeSlots) return fail("recv offset %lld out of range", recv_dst[k]);
+    Neighbor nb;
+    nb.rank = neig_rank;
+    nb.sendCount = n_send;
+    nb.recvCount = n_recv;
+    if (n_send) {
+        CUDA_OK(cudaMalloc(&nb.d_sendSrc, (size_t)n_send * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(nb.d_sendSrc, send_src, (size_t)n_send * sizeof(long long), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&nb.d_sendBuf, (size_t)n_send * c->nFields * sizeof(double)));
+    }
+    if (n_recv) {
+        CUDA_OK(cudaMalloc(&nb.d_recvDst, (size_t)n_recv * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(nb.d_recvDst, recv_dst, (size_t)n_recv * sizeof(long long), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&nb.d_recvBuf, (size_t)n_recv * c->nFields * sizeof(double)));
+    }
+    c->nbrs.push_back(std::move(nb));
+    return 0;
+}
+
+int chimp_set_boundary_count(chimp_lattice *c, int n_boundary)
+{
+    if (check(c, true)) return 1;
+    if (n_boundary < 0 || n_boundary > c->n) return fail("boundary count out of range");
+    c->nBoundary = std::min(((n_boundary + 31) / 32) * 32, c->n);
+    return 0;
+}
 int chimp_set_exchange_callback(chimp_lattice *c, chimp_exchange_fn fn, void *user)
 {
     if (!c) return fail("null lattice handle");
@@ -1213,7 +1285,7 @@ double chimp_index_bytes_per_node(chimp_lattice *c)
 {
     if (!c || c->n == 0) return 0.0;
     if (c->indexForm == CHIMP_INDEX_TABLE) return 4.0 * c->li.nQ;
-    return (4.0 * c->nWords * c->nPad + 4.0 * c->nTiles * c->li.nQ + 128.0 * c->nRows) / c->n;
+    return (4.0 * c->nWords * c->nPad + 16.0 * c->nTiles * c->nWords + 128.0 * c->nRows) / c->n;
 }
 long long chimp_plane_stride(chimp_lattice *c) { return c ? c->stride : 0; }
 

@@ -92,22 +92,37 @@ __global__ void classifyTilesKernel(const int32_t *__restrict__ table, int n, in
     // byte (q & 3) of word (q >> 2) of node i
     deltaBytes[((long long)(q >> 2) * nPad + i) * 4 + (q & 3)] = (uint8_t)((bounce || !regular) ? 255 : (t - b0));
     if (lane == 0) {
-        if (regular) base[(long long)q * nTiles + tile] = b0;
-        else base[(long long)q * nTiles + tile] = -(atomicAdd(irregularCount, 1) + 1);
+        const int nSlots = ((nQ + 3) / 4) * 4; // tile-major, padded to whole int4 groups
+        if (regular) base[(long long)tile * nSlots + q] = b0;
+        else base[(long long)tile * nSlots + q] = -(atomicAdd(irregularCount, 1) + 1);
     }
 }
 
+// kernel form of the pull table: -1 (reversed own slot) becomes i + (rev q - q) * stride
+__global__ void kernelTableKernel(const int32_t *__restrict__ table, int32_t *__restrict__ ktable, int n, int nPad,
+                                  int nQ, int nPairs, long long stride)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (long long)nQ * nPad) return;
+    const int q = (int)(k / nPad), i = (int)(k % nPad);
+    const int rq = q == nQ - 1 ? q : (q + nPairs) % (nQ - 1);
+    const int t = i < n ? table[k] : i;
+    ktable[k] = t >= 0 ? t : (int)(i + (long long)(rq - q) * stride);
+}
+
 __global__ void fillRowsKernel(const int32_t *__restrict__ table, int n, int nPad, int nQ, int nTiles,
-                               const int32_t *__restrict__ base, int32_t *__restrict__ rows)
+                               const int32_t *__restrict__ base, int32_t *__restrict__ rows, int nPairs, long long stride)
 {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
     if (warp >= (long long)nTiles * nQ) return;
     const int q = (int)(warp / nTiles), tile = (int)(warp % nTiles);
-    const int b = base[(long long)q * nTiles + tile];
+    const int b = base[(long long)tile * (((nQ + 3) / 4) * 4) + q];
     if (b >= 0) return;
     const int i = tile * 32 + lane;
-    rows[((long long)(-b - 1) << 5) + lane] = (i < n) ? table[(long long)q * nPad + i] : -1;
+    const int rq = q == nQ - 1 ? q : (q + nPairs) % (nQ - 1);
+    const int t = (i < n) ? table[(long long)q * nPad + i] : i;
+    rows[((long long)(-b - 1) << 5) + lane] = t >= 0 ? t : (int)(i + (long long)(rq - q) * stride);
 }
 
 } // namespace chimp

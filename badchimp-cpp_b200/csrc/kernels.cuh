@@ -28,26 +28,36 @@ namespace chimp {
 
 // launch shape of the collide-stream kernels (tuned on B200)
 #ifndef CHIMP_BLOCK
-#define CHIMP_BLOCK 256
+#define CHIMP_BLOCK 128
 #endif
 #ifndef CHIMP_MIN_BLOCKS
-#define CHIMP_MIN_BLOCKS 3
+#define CHIMP_MIN_BLOCKS 6
 #endif
 
 enum { COLL_BGK = 0, COLL_TRT = 1 };
 enum { IDX_TABLE = 0, IDX_COMPACT = 1 };
 
+// The step kernels address one plane as  in[q] + s  with a signed 32-bit slot index s.  A bounce
+// (reversed own slot X[rev q][i]) is expressed in the same form: s = i + (rev q - q) * stride,
+// so the hot path has no select between two planes.  "Kernel form" below means T with its -1
+// entries replaced that way.
 struct IndexView {
-    const int32_t *table;    // IDX_TABLE: [nQ][nPad]
-    const uint32_t *delta;   // IDX_COMPACT : [nWords][nPad], byte (q & 3) of word (q >> 2): source - base, 255 = bounce
-    const int32_t *base;     // IDX_COMPACT : [nQ][nTiles]; >= 0 smallest source of the tile, < 0: -(row+1) into `rows`
-    const int32_t *rows;     // IDX_COMPACT : explicit rows [nRows][32] (-1 = bounce)
+    const int32_t *table;    // IDX_TABLE  : [nQ][nPad] kernel form
+    const uint32_t *delta;   // IDX_COMPACT: [nWords][nPad], byte (q & 3) of word (q >> 2): source - base, 255 = bounce
+    const int32_t *base;     // IDX_COMPACT: [nTiles][4*nWords] (16-byte aligned per tile); >= 0 smallest source of
+                             //              the tile for direction q, < 0: -(row+1) into `rows`
+    const int32_t *rows;     // IDX_COMPACT: explicit rows [nRows][32], kernel form
     int nTiles;
+    int bounceOff[27];       // (rev q - q) * stride
+};
+
+struct Planes {
+    const double *in[27];    // field 0, plane q of the buffer being read
+    double *out[27];         // field 0, plane q of the buffer being written
 };
 
 struct StepArgs {
-    const double *fin;
-    double *fout;
+    Planes pl;
     long long stride;   // doubles per (field,q) plane
     int n;              // own nodes
     int nPad;           // padded own nodes (multiple of 32)
@@ -88,59 +98,59 @@ __device__ __forceinline__ void staticFor(F &f)
     staticForImpl(f, std::make_integer_sequence<int, N>{});
 }
 
-// Resolves, for node i and every direction q, where f_q(i) lives in one field's planes
-// (offset in doubles from the field base) and hands it to fn(q, offset).  `a` is any argument
-// block with stride / nPad / idx members.  All 32 lanes of a warp must call this together in
-// IDX_COMPACT form; dead lanes pass live = false and get offset 0.
+// Resolves, for node i and every direction q, the address of f_q(i) in field 0 of the buffer
+// being read and hands it to fn(q, pointer).  `a` is any argument block with pl / nPad / idx
+// members.  Dead lanes (live == false) get the plane base and must not dereference it.
 template <class L, int IDX, class Args, class Fn>
 __device__ __forceinline__ void forEachSource(const Args &a, int i, bool live, Fn &&fn)
 {
     if (IDX == IDX_TABLE) {
         int src[L::nQ];
 #pragma unroll
-        for (int q = 0; q < L::nQ; ++q) src[q] = live ? __ldg(a.idx.table + (long long)q * a.nPad + i) : 0;
+        for (int q = 0; q < L::nQ; ++q) src[q] = live ? __ldg(a.idx.table + ((unsigned)q * (unsigned)a.nPad + (unsigned)i)) : 0;
 #pragma unroll
-        for (int q = 0; q < L::nQ; ++q) {
-            const int s = src[q];
-            const long long off = (s >= 0) ? (long long)q * a.stride + s : (long long)reverseDir<L>(q) * a.stride + i;
-            fn(q, live ? off : 0ll);
-        }
+        for (int q = 0; q < L::nQ; ++q) fn(q, a.pl.in[q] + src[q]);
     } else {
         constexpr int NW = (L::nQ + 3) / 4;
-        const int tile = i >> 5;
-        const unsigned lane = threadIdx.x & 31u;
-        // every index word of the node / tile is requested before anything waits on one
+        const int tile = min(i >> 5, a.idx.nTiles - 1);
+        // every index word of the node and of its tile is requested before anything waits on one:
+        // NW coalesced words of delta bytes, and the tile's bases as NW broadcast 16-byte loads
         uint32_t wd[NW];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) wd[w] = live ? __ldg(a.idx.delta + (long long)w * a.nPad + i) : 0xffffffffu;
-        int base[L::nQ];
-        const int tl = min(tile, a.idx.nTiles - 1);
+        for (int w = 0; w < NW; ++w) wd[w] = live ? __ldg(a.idx.delta + ((unsigned)w * (unsigned)a.nPad + (unsigned)i)) : 0u;
+        const int4 *bp = reinterpret_cast<const int4 *>(a.idx.base) + (unsigned)tile * NW;
+        int base[NW * 4];
 #pragma unroll
-        for (int q = 0; q < L::nQ; ++q) base[q] = __ldg(a.idx.base + (long long)q * a.idx.nTiles + tl);
+        for (int g = 0; g < NW; ++g) {
+            const int4 v = __ldg(bp + g);
+            base[4 * g] = v.x; base[4 * g + 1] = v.y; base[4 * g + 2] = v.z; base[4 * g + 3] = v.w;
+        }
+        int s[L::nQ];
+        int anyRow = 0;
 #pragma unroll
         for (int q = 0; q < L::nQ; ++q) {
-            const int b = base[q];
             const int d = (int)((wd[q >> 2] >> (8 * (q & 3))) & 0xffu);
-            int s = b + d;
-            bool bounce = d == 255;
-            if (b < 0) { // warp-uniform: this (tile, q) keeps an explicit row
-                s = live ? __ldg(a.idx.rows + ((long long)(-b - 1) << 5) + lane) : 0;
-                bounce = s < 0;
-            }
-            const long long off = bounce ? (long long)reverseDir<L>(q) * a.stride + i : (long long)q * a.stride + s;
-            fn(q, live ? off : 0ll);
+            s[q] = (d == 255) ? i + a.idx.bounceOff[q] : base[q] + d;
+            anyRow |= base[q];
         }
+        if (anyRow < 0) { // warp-uniform and rare: some (tile, q) of this tile keeps an explicit row
+            const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+            for (int q = 0; q < L::nQ; ++q)
+                if (base[q] < 0) s[q] = __ldg(a.idx.rows + (((unsigned)(-base[q] - 1) << 5) + lane));
+        }
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) fn(q, a.pl.in[q] + (live ? s[q] : 0));
     }
 }
 
 template <class L, int IDX>
 struct Gather {
-    // loads f_q(n) for all q of node i (lane = i & 31) from the field starting at fin
+    // loads f_q(n) for all q of node i (lane = i & 31); fieldOff = offset of the field in doubles
     template <class Args>
-    __device__ __forceinline__ static void load(const Args &a, const double *__restrict__ fin, int i, bool live,
-                                                double (&f)[L::nQ])
+    __device__ __forceinline__ static void load(const Args &a, long long fieldOff, int i, bool live, double (&f)[L::nQ])
     {
-        forEachSource<L, IDX>(a, i, live, [&](int q, long long off) { f[q] = live ? __ldg(fin + off) : 0.0; });
+        forEachSource<L, IDX>(a, i, live, [&](int q, const double *p) { f[q] = live ? __ldg(p + fieldOff) : 0.0; });
     }
 };
 
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
     if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return; // whole warp out of range
 
     double f[L::nQ];
-    Gather<L, IDX>::load(a, a.fin, i, live, f);
+    Gather<L, IDX>::load(a, 0ll, i, live, f);
     if (!live) return;
 
     double rho = nodeRho<L>(f);
@@ -186,7 +196,6 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
     const double uF = dotD<L>(u, F);
     uint32_t pm = 0;
     if (ONEPHASE && a.pmask) pm = a.pmask[i];
-    double *const fout = a.fout + i;
 
     // Opposite directions are collided together.  With c_r = -c_q every intermediate of the
     // reversed direction is the exact IEEE negation (c.u, c.F, 3 c.u, 3 c.F, the TRT odd part) or
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
             // the node's own reversed direction, so it can carry the boundary value directly
             v = -v + 2 * chimp_w<L>(q) * a.rhoW * (1 + 0.5 * (kC4Inv * cu * cu - kC2Inv * u2));
         }
-        fout[(long long)q * a.stride] = v;
+        a.pl.out[q][i] = v;
     };
     auto pairBody = [&](auto pc) {
         constexpr int q = decltype(pc)::value, r = q + L::nPairs;
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(256) massChangeKernel(const StepArgs a, int nL
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.n;
     double f[L::nQ];
-    Gather<L, IDX>::load(a, a.fin, live ? i : 0, live, f);
+    Gather<L, IDX>::load(a, 0ll, live ? i : 0, live, f);
     const double val = live ? 1.0 - nodeRho<L>(f) : 0.0;
     const int lab = live ? a.label[i] : -1;
     for (int l = 0; l < nLabels; ++l) {
@@ -320,8 +329,7 @@ __global__ void massFinalizeKernel(const double *__restrict__ partial, int nBloc
 // zero slot for every other neighbour (cgField is zero-initialised there).
 // ---------------------------------------------------------------------------------------
 struct TwoPhaseArgs {
-    const double *fin;
-    double *fout;
+    Planes pl;
     long long stride;
     int n, nPad, begin, end;
     IndexView idx;
@@ -342,10 +350,10 @@ __global__ void __launch_bounds__(256) phaseMomentsKernel(const TwoPhaseArgs a)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.n;
     double f0[L::nQ], f1[L::nQ];
-    const double *fin1 = a.fin + (long long)L::nQ * a.stride;
-    forEachSource<L, IDX>(a, live ? i : 0, live, [&](int q, long long off) {
-        f0[q] = live ? __ldg(a.fin + off) : 0.0;
-        f1[q] = live ? __ldg(fin1 + off) : 0.0;
+    const long long field1 = (long long)L::nQ * a.stride;
+    forEachSource<L, IDX>(a, live ? i : 0, live, [&](int q, const double *p) {
+        f0[q] = live ? __ldg(p) : 0.0;
+        f1[q] = live ? __ldg(p + field1) : 0.0;
     });
     double mom = 0.0;
     if (live) {
@@ -372,9 +380,9 @@ __global__ void __launch_bounds__(256) twoPhaseCollideKernel(const TwoPhaseArgs 
     if (IDX == IDX_TABLE && !live) return;
     if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return;
     double fTot[L::nQ];
-    const double *fin1 = a.fin + (long long)L::nQ * a.stride;
-    forEachSource<L, IDX>(a, i, live, [&](int q, long long off) {
-        fTot[q] = live ? __ldg(a.fin + off) + __ldg(fin1 + off) : 0.0;
+    const long long field1 = (long long)L::nQ * a.stride;
+    forEachSource<L, IDX>(a, i, live, [&](int q, const double *p) {
+        fTot[q] = live ? __ldg(p) + __ldg(p + field1) : 0.0;
     });
     if (!live) return;
     const double rho0 = a.rho[i], rho1 = a.rho[(long long)a.nPad + i];
@@ -408,7 +416,6 @@ __global__ void __launch_bounds__(256) twoPhaseCollideKernel(const TwoPhaseArgs 
     const double AF0_5 = 1.125 * CGNorm * a.sigma / tau;      // LBcollision2phase.h:12
     const double rhoFacBeta = a.beta * rho0 * rho1 / rho;     // LBcollision2phase.h:74
     const double c0 = (rho0 / rho), c1 = (rho1 / rho);
-    double *fout1 = a.fout + (long long)L::nQ * a.stride;
     auto body = [&](auto qc) {
         constexpr int q = decltype(qc)::value;
         const double cu = cDot<L, q>(u);
@@ -425,8 +432,8 @@ __global__ void __launch_bounds__(256) twoPhaseCollideKernel(const TwoPhaseArgs 
             rc = 0.0;
         }
         const double common = fTot[q] + om + dF + st;
-        a.fout[(long long)q * a.stride + i] = c0 * common + rc;
-        fout1[(long long)q * a.stride + i] = c1 * common - rc;
+        a.pl.out[q][i] = c0 * common + rc;
+        a.pl.out[q][field1 + i] = c1 * common - rc;
     };
     staticFor<L::nQ>(body);
 }

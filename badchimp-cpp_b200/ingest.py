@@ -93,3 +93,89 @@ def sphere_pack_slab(shape, radius, porosity, seed, z0, z1):
             block[inside] = 0
             geo[sub] = block
     return geo
+
+
+def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: bool = True):
+    """One rank of a z-slab decomposition (periodic in x, y; z neighbours are other ranks).
+
+    fluid_ext: bool [nx, ny, nz + 2]: the rank's own slab plus one halo layer below (index 0) and
+    above (index -1) taken from the neighbour ranks.  Own fluid nodes are labelled 1..N in C-order
+    (the reference's per-rank numbering, vtklb.py:92-94).  Device slots: nodes of the first and
+    last z-layer first (they are the only halo-coupled ones) when boundary_first.
+
+    Returns dict(table int32 [nQ, n_pad], labels int32 [n_pad], n, n_pad, n_halo, n_boundary,
+    faces = {"down": (send_src, recv_dst), "up": (send_src, recv_dst)}) with int64 slot offsets
+    q*stride + slot.  Message order of a face: directions ascending, receiver cells in C-order of (x, y).
+    """
+    basis = G.BASIS[lattice]
+    nq, nd = basis.shape
+    assert nd == 3 and fluid_ext.dim() == 3
+    dev = fluid_ext.device
+    fluid_ext = fluid_ext.bool()
+    own = fluid_ext[:, :, 1:-1]
+    lower, upper = fluid_ext[:, :, 0], fluid_ext[:, :, -1]
+    nz = own.shape[2]
+    flat = own.reshape(-1)
+    n = int(flat.sum().item())
+    n_pad = ((n + 31) // 32) * 32
+    label = (torch.cumsum(flat, 0, dtype=torch.int32) * flat).reshape(own.shape)
+    own_idx = torch.nonzero(flat).reshape(-1)                 # flat cell index of label 1..n
+    if boundary_first:
+        z_of = own_idx % nz
+        is_b = (z_of == 0) | (z_of == nz - 1)
+        order = torch.cat([torch.nonzero(is_b).reshape(-1), torch.nonzero(~is_b).reshape(-1)])  # label-1 per slot
+        n_boundary = int(is_b.sum().item())
+    else:
+        order = torch.arange(n, device=dev)
+        n_boundary = 0
+    slot_of_label = torch.full((n + 1,), -1, dtype=torch.int32, device=dev)
+    slot_of_label[order + 1] = torch.arange(n, dtype=torch.int32, device=dev)
+    slot_grid = slot_of_label[label.long()]                    # -1 on solid cells
+    cells_by_slot = own_idx[order]                             # flat own-cell index per slot
+
+    def shift2(a, cx, cy):
+        return torch.roll(a, shifts=(cx, cy), dims=(0, 1)) if (cx or cy) else a
+
+    # halo element counts per direction
+    recv_mask, counts = {}, [0] * nq
+    for q in range(nq):
+        cx, cy, cz = (int(v) for v in basis[q])
+        if cz == 1:
+            m = own[:, :, 0] & shift2(lower, cx, cy)
+        elif cz == -1:
+            m = own[:, :, -1] & shift2(upper, cx, cy)
+        else:
+            continue
+        recv_mask[q] = m
+        counts[q] = int(m.sum().item())
+    n_halo = ((max(counts) + 15) // 16) * 16
+    stride = n_pad + n_halo
+    table = torch.full((nq, n_pad), -1, dtype=torch.int32, device=dev)
+    faces = {"down": ([], []), "up": ([], [])}
+    for q in range(nq):
+        cx, cy, cz = (int(v) for v in basis[q])
+        src = torch.roll(slot_grid, shifts=(cx, cy, cz), dims=(0, 1, 2)) if (cx or cy or cz) else slot_grid
+        if cz != 0:
+            src = src.clone()
+            m = recv_mask[q]
+            k = torch.cumsum(m.reshape(-1), 0, dtype=torch.int32).reshape(m.shape) - 1
+            layer = torch.where(m, n_pad + k, torch.full_like(k, -1))
+            if cz == 1:
+                src[:, :, 0] = layer
+                # I receive direction q from the rank below; the rank above receives it from my top layer
+                faces["down"][1].append(q * stride + n_pad + torch.arange(counts[q], device=dev, dtype=torch.int64))
+                ms = upper & shift2(own[:, :, -1], cx, cy)
+                faces["up"][0].append(q * stride + shift2(slot_grid[:, :, -1], cx, cy)[ms].long())
+            else:
+                src[:, :, -1] = layer
+                faces["up"][1].append(q * stride + n_pad + torch.arange(counts[q], device=dev, dtype=torch.int64))
+                ms = lower & shift2(own[:, :, 0], cx, cy)
+                faces["down"][0].append(q * stride + shift2(slot_grid[:, :, 0], cx, cy)[ms].long())
+        table[q, :n] = src.reshape(-1)[cells_by_slot]
+        del src
+    labels = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+    labels[:n] = (order + 1).to(torch.int32)
+    cat = lambda l: torch.cat(l) if l else torch.zeros(0, dtype=torch.int64, device=dev)
+    faces = {k: (cat(v[0]), cat(v[1])) for k, v in faces.items()}
+    return dict(table=table, labels=labels, n=n, n_pad=n_pad, n_halo=n_halo, n_boundary=n_boundary, faces=faces,
+                stride=stride)

@@ -1,0 +1,165 @@
+"""N ranks, one process per GPU: z-slab decomposition with halo exchange over torch.distributed.
+
+Replaces MonLatMpi::communicateLbField (src/lbsolver/LBmonlatmpi.h:236-297): the engine packs
+the outgoing populations of the two z-faces on the device (haloPackKernel), this module moves
+the packed buffers with NCCL send/recv on the engine's halo stream while the interior nodes
+are still being collided, and the engine unpacks them into the halo-in slots.
+
+The z direction is periodic, so the ranks form a ring: face "down" talks to rank-1, face "up"
+to rank+1.  With 2 ranks both faces talk to the same peer; messages between one pair of ranks
+are matched in posting order, so sends are posted (down, up) and receives (up, down): the
+peer's "down" message is what arrives at my "up" face.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class RingHalo:
+    """send/recv buffers of the two z-faces and the exchange itself (works on CPU/gloo and CUDA/NCCL)"""
+
+    def __init__(self, rank, world, n_send_down, n_recv_down, n_send_up, n_recv_up, device):
+        self.rank, self.world = rank, world
+        self.down, self.up = (rank - 1) % world, (rank + 1) % world
+        mk = lambda n: torch.zeros(max(int(n), 1), dtype=torch.float64, device=device)
+        self.send_down, self.recv_down = mk(n_send_down), mk(n_recv_down)
+        self.send_up, self.recv_up = mk(n_send_up), mk(n_recv_up)
+        self.counts = (int(n_send_down), int(n_recv_down), int(n_send_up), int(n_recv_up))
+
+    def ops(self):
+        sd, rd, su, ru = self.counts
+        return [dist.P2POp(dist.isend, self.send_down[:sd], self.down),
+                dist.P2POp(dist.isend, self.send_up[:su], self.up),
+                dist.P2POp(dist.irecv, self.recv_up[:ru], self.up),
+                dist.P2POp(dist.irecv, self.recv_down[:rd], self.down)]
+
+    def exchange(self):
+        reqs = dist.batch_isend_irecv(self.ops())
+        for r in reqs:
+            r.wait()
+
+
+def attach_ring(lat, slab, rank, world, device):
+    """registers the two halo faces of a structured-ingest lattice and wires the NCCL exchange"""
+    faces = slab["faces"]
+    lat.add_halo_face((rank - 1) % world, faces["down"][0].cpu().numpy(), faces["down"][1].cpu().numpy())
+    lat.add_halo_face((rank + 1) % world, faces["up"][0].cpu().numpy(), faces["up"][1].cpu().numpy())
+    lat.set_boundary_count(slab["n_boundary"])
+    ring = RingHalo(rank, world, len(faces["down"][0]), len(faces["down"][1]), len(faces["up"][0]), len(faces["up"][1]), device)
+    lat.set_halo_buffers(0, ring.send_down.data_ptr(), ring.recv_down.data_ptr())
+    lat.set_halo_buffers(1, ring.send_up.data_ptr(), ring.recv_up.data_ptr())
+
+    def on_exchange(stream_ptr):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr)):
+            ring.exchange()
+
+    lat.set_exchange_callback(on_exchange)
+    lat._ring = ring
+    return ring
+
+
+def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
+    """bench.py --gpus N (N > 1): every rank owns one size^3 block of a size x size x (size N) pack"""
+    from . import bench_impl as B
+    capi = pkg.capi
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    t_setup = time.perf_counter()
+    gshape = (size, size, size * world)
+    ext = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, rank * size - 1, (rank + 1) * size + 1)
+    slab = ingest.build_slab_tables(torch.from_numpy(ext).to(device).bool(), lattice, boundary_first=True)
+    index_form = capi.INDEX_COMPACT if args.index == "compact" else capi.INDEX_TABLE
+    lat = capi.lattice_from_device_table(lattice, slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
+                                         slab["labels"].data_ptr(), 1, index_form, local)
+    attach_ring(lat, slab, rank, world, device)
+    n = slab["n"]
+    slab["table"] = slab["labels"] = None
+    torch.cuda.empty_cache()
+    lat.init_uniform(1.0)
+    setup_s = time.perf_counter() - t_setup
+
+    def total(x, op=dist.ReduceOp.SUM):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    n_total = total(n)
+    lat.step_single(args.warmup, tau=tau, force=force)
+    lat.synchronize()
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=B._clock_sampler, args=(stop, samples), daemon=True)
+    if rank == 0:
+        th.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    l1 = capi.lib().chimp_launch_count()
+    ms = lat.step_timed(args.steps, tau=tau, force=force)
+    lat.synchronize()
+    l2 = capi.lib().chimp_launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms_max = total(ms, dist.ReduceOp.MAX)
+    if rank == 0:
+        t_extra = time.perf_counter()
+        while len(samples) < 6 and time.perf_counter() - t_extra < 2.0:
+            time.sleep(0.1)
+    # keep all ranks in step while rank 0 samples clocks under load
+    lat.step_single(20, tau=tau, force=force)
+    lat.synchronize()
+    stop.set()
+    rho, _ = lat.download_moments_device_order()
+    mass_err = abs(total(rho.sum()) / n_total - 1.0)
+
+    # end to end per rank: upload LbField (pinned host, reference AoS rows 0..N), K steps, download rho + vel
+    e2e = None
+    try:
+        nq = len(pkg.geometry.BASIS[lattice])
+        host_f = torch.empty((n + 1, nq), dtype=torch.float64, pin_memory=True)
+        host_f[:] = torch.from_numpy(pkg.cases.lattice_weights(lattice))[None, :]
+        host_rho = torch.empty((n + 1,), dtype=torch.float64, pin_memory=True)
+        host_vel = torch.empty((n + 1, 3), dtype=torch.float64, pin_memory=True)
+        lib = capi.lib()
+        p = lat._single_params(tau, force, None)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        capi._check(lib.chimp_upload_lbfield(lat.h, C.c_void_p(host_f.data_ptr())))
+        capi._check(lib.chimp_step_single(lat.h, C.byref(p), C.c_int(args.steps)))
+        capi._check(lib.chimp_download_rho(lat.h, C.c_void_p(host_rho.data_ptr()), C.c_int(1)))
+        capi._check(lib.chimp_download_vel(lat.h, C.c_void_p(host_vel.data_ptr())))
+        dt = total(time.perf_counter() - t0, dist.ReduceOp.MAX)
+        e2e = {"value": n_total * args.steps / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": total(host_f.numel() * 8) / args.steps,
+               "d2h_bytes_per_step": total((host_rho.numel() + host_vel.numel()) * 8) / args.steps,
+               "cycle": "per rank: upload LbField (pinned host, reference AoS) + %d steps with halo exchange + download rho, vel; wall clock, max over ranks" % args.steps}
+    except Exception as exc:  # pragma: no cover
+        e2e = {"value": None, "unit": "MLUPS", "error": str(exc)}
+
+    if rank == 0:
+        peak, peak_src = B._peaks()
+        kernel_ms = ms_max / args.steps
+        achieved = B.B_ALG[lattice] * n_total / world / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": "MLUPS", "value": n_total * args.steps / (ms_max * 1e-3) / 1e6, "unit": "MLUPS", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "std_case physics (D3Q19 BGK + Guo force + half-way bounce back), periodic random sphere pack %dx%dx%d (one %d^3 block per GPU, z-slabs), R=%d, seed 1234" % (size, size, size * world, size, size // 8),
+                           "fluid_nodes": n_total, "index_form": args.index, "parallelism": "z-slab x%d, NCCL send/recv halos overlapped with interior nodes" % world,
+                           "l2_policy": "state per GPU 2 x %.1f GB >> 126 MB L2" % (n * 152 / 1e9),
+                           "halo_bytes_per_step_per_gpu": 8.0 * (sum(lat._ring.counts[0::2])),
+                           "setup_seconds": setup_s, "mean_rho_error": mass_err},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "per": "GPU (mean)"},
+                "e2e": e2e, "gpu_launches": int(l2 - l1), "clocks": B._summarize_clocks(samples)}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -155,6 +155,13 @@ void *chimp_recv_buffer_dev(chimp_lattice *, int k);
 /* let the engine pack into / unpack from caller-owned device buffers (e.g. torch tensors used with NCCL) */
 int chimp_set_halo_buffers(chimp_lattice *, int k, void *send_dev, void *recv_dev);
 void *chimp_halo_stream(chimp_lattice *);
+/* structured-ingest lattices (chimp_create_from_device_table): one halo face towards neig_rank.
+ * send_src / recv_dst are slot offsets q*plane_stride + slot inside one field (host arrays);
+ * their order defines the packed message.  The same rank may own two faces (2-rank ring). */
+int chimp_add_halo_face(chimp_lattice *, int neig_rank, long long n_send, const long long *send_src,
+                        long long n_recv, const long long *recv_dst);
+/* the first n_boundary slots hold the halo-coupled nodes: they are stepped and packed first */
+int chimp_set_boundary_count(chimp_lattice *, int n_boundary);
 typedef int (*chimp_exchange_fn)(void *user, void *stream);
 /* called once per step after the boundary nodes were packed, on the halo stream */
 int chimp_set_exchange_callback(chimp_lattice *, chimp_exchange_fn fn, void *user);
