@@ -1,0 +1,13 @@
+// Umbrella header, the counterpart of the reference's src/LBSOLVER.h for the hot path.
+#ifndef CHIMP_LBSOLVER_LIB
+#define CHIMP_LBSOLVER_LIB
+#include "LBglobal.h"
+#include "LBlattices.h"
+#include "LBfield.h"
+#include "LBvtk.h"
+#include "LBgrid.h"
+#include "LBhalfwaybb.h"
+#include "LBbndmpi.h"
+#include "LBgpu.h"
+#include "Input.h"
+#endif

@@ -1,0 +1,84 @@
+// GpuLattice<DXQY>: the reference's objects handed to the C-ABI engine (include/chimp_b200.h).
+// It replaces, in a main, the per-node loop + swapData + communicateLbField + boundary apply().
+#ifndef CHIMP_LBGPU_H
+#define CHIMP_LBGPU_H
+
+#include "../../../include/chimp_b200.h"
+#include "LBbndmpi.h"
+#include "LBfield.h"
+#include "LBhalfwaybb.h"
+
+inline void chimpCheck(int rc)
+{
+    if (rc) chimp_host::die(std::string("GPU engine: ") + chimp_last_error());
+}
+
+template <typename DXQY>
+class GpuLattice
+{
+public:
+    GpuLattice(const Grid<DXQY> &grid, const std::vector<int> &bulkNodes, int nFields, int device = -1) : nNodes_(grid.size())
+    {
+        chimpCheck(chimp_create(&h_, DXQY::chimpId, grid.size(), grid.neighborList().data(), int(bulkNodes.size()),
+                                bulkNodes.data(), nFields, device));
+    }
+    ~GpuLattice() { chimp_destroy(h_); }
+    GpuLattice(const GpuLattice &) = delete;
+    GpuLattice &operator=(const GpuLattice &) = delete;
+
+    void add(const HalfWayBounceBack<DXQY> &bb)
+    {
+        chimpCheck(chimp_add_halfway_bb(h_, bb.size(), bb.nodeList().data(), bb.nBetaList().data(), bb.nGammaList().data(),
+                                        bb.nDeltaList().data(), bb.linkList().data()));
+    }
+    void add(const BndMpi<DXQY> &mpi)
+    {
+        for (const MonLatLists &m : mpi.lists())
+            chimpCheck(chimp_add_neighbor(h_, m.neigRank, int(m.nodesToSend.size()), m.nodesToSend.data(), m.nDirPerNodeToSend.data(),
+                                          m.dirListToSend.data(), int(m.nodesReceived.size()), m.nodesReceived.data(),
+                                          m.nDirPerNodeReceived.data(), m.dirListReceived.data()));
+    }
+    // link lists {nodeFluid, qUnknown, nodeWall, qKnown} of std_one_phase (main.cpp:27-126)
+    void addLinks(int kind, const std::vector<std::vector<int>> &links)
+    {
+        std::vector<int32_t> flat;
+        for (const auto &l : links) flat.insert(flat.end(), l.begin(), l.end());
+        chimpCheck(chimp_add_links(h_, kind, int(links.size()), flat.data()));
+    }
+    void setSolidBoundary(const std::vector<int> &nodes) { chimpCheck(chimp_set_solid_boundary(h_, int(nodes.size()), nodes.data())); }
+    void finalize(int indexForm = CHIMP_INDEX_COMPACT, bool boundaryFirst = true) { chimpCheck(chimp_finalize(h_, indexForm, boundaryFirst)); }
+
+    void upload(LbField<DXQY> &f) { chimpCheck(chimp_upload_lbfield(h_, f.data())); }
+    void download(LbField<DXQY> &f) { chimpCheck(chimp_download_lbfield(h_, f.data())); }
+    void download(ScalarField &rho, VectorField<DXQY> &vel)
+    {
+        chimpCheck(chimp_download_rho(h_, rho.data(), rho.num_fields()));
+        chimpCheck(chimp_download_vel(h_, vel.data()));
+    }
+    // nSteps iterations of std_case/main.cpp:110-145 with calcOmegaBGK + calcDeltaOmegaF
+    void stepBGK(lbBase_t tau, const std::valarray<lbBase_t> &bodyForce, int nSteps)
+    {
+        chimp_single_params p{};
+        p.collision = CHIMP_BGK;
+        p.tau = tau;
+        for (int d = 0; d < DXQY::nD; ++d) p.force[d] = bodyForce[d];
+        chimpCheck(chimp_step_single(h_, &p, nSteps));
+    }
+    // same with calcOmegaBGKTRT + calcDeltaOmegaFTRT(phi = 1)
+    void stepTRT(lbBase_t tauSym, lbBase_t tauAnti, const std::valarray<lbBase_t> &bodyForce, int nSteps)
+    {
+        chimp_single_params p{};
+        p.collision = CHIMP_TRT;
+        p.tau_sym = tauSym;
+        p.tau_anti = tauAnti;
+        for (int d = 0; d < DXQY::nD; ++d) p.force[d] = bodyForce[d];
+        chimpCheck(chimp_step_single(h_, &p, nSteps));
+    }
+    chimp_lattice *handle() { return h_; }
+
+private:
+    chimp_lattice *h_ = nullptr;
+    int nNodes_;
+};
+
+#endif
