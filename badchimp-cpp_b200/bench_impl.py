@@ -152,6 +152,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # NCCL kernels ahead of the interior blocks
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     size = args.size or 512
     lattice = "D3Q19"

@@ -38,6 +38,7 @@ class TwoPhaseParams(C.Structure):
 
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 
 # every symbol include/chimp_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -52,7 +53,8 @@ SYMBOLS = [
     "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_irregular_fraction",
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
-    "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count",
+    "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
+    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
 ]
 
 
@@ -78,6 +80,9 @@ def lib():
         l.chimp_send_buffer_dev.argtypes = [C.c_void_p, C.c_int]
         l.chimp_recv_buffer_dev.restype = C.c_void_p
         l.chimp_recv_buffer_dev.argtypes = [C.c_void_p, C.c_int]
+        for name in ("chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev"):
+            getattr(l, name).restype = C.c_void_p
+            getattr(l, name).argtypes = [C.c_void_p, C.c_int]
         l.chimp_halo_stream.restype = C.c_void_p
         l.chimp_halo_stream.argtypes = [C.c_void_p]
         l.chimp_set_halo_buffers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -332,6 +337,41 @@ class Lattice:
                 return 1
         self._cb = EXCHANGE_FN(tramp)
         _check(lib().chimp_set_exchange_callback(self.h, self._cb, None))
+
+    def set_scalar_exchange_callback(self, fn):
+        """fn(stream_ptr) moves the packed phi values of every neighbour (scalar halo)"""
+        def tramp(_user, stream):
+            try:
+                fn(int(stream) if stream else 0)
+                return 0
+            except Exception as exc:  # pragma: no cover
+                print("scalar exchange callback failed:", exc)
+                return 1
+        self._cb_scalar = EXCHANGE_FN(tramp)
+        _check(lib().chimp_set_scalar_exchange_callback(self.h, self._cb_scalar, None))
+
+    def set_allreduce_callback(self, fn):
+        """fn(dev_ptr, count, stream_ptr) sums `count` doubles at dev_ptr over all ranks, in place"""
+        def tramp(_user, dev, count, stream):
+            try:
+                fn(int(dev), int(count), int(stream) if stream else 0)
+                return 0
+            except Exception as exc:  # pragma: no cover
+                print("allreduce callback failed:", exc)
+                return 1
+        self._cb_allreduce = ALLREDUCE_FN(tramp)
+        _check(lib().chimp_set_allreduce_callback(self.h, self._cb_allreduce, None))
+
+    def scalar_neighbor_info(self, k):
+        ns, nr = C.c_longlong(), C.c_longlong()
+        _check(lib().chimp_scalar_neighbor_info(self.h, C.c_int(k), C.byref(ns), C.byref(nr)))
+        return ns.value, nr.value
+
+    def scalar_send_buffer_ptr(self, k):
+        return lib().chimp_scalar_send_buffer_dev(self.h, C.c_int(k))
+
+    def scalar_recv_buffer_ptr(self, k):
+        return lib().chimp_scalar_recv_buffer_dev(self.h, C.c_int(k))
 
     def set_stream(self, ptr):
         _check(lib().chimp_set_stream(self.h, C.c_void_p(ptr)))

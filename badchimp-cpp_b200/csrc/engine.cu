@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <climits>
 #include <string>
 #include <vector>
 
@@ -74,6 +75,9 @@ struct Neighbor {
     std::vector<int32_t> sendNodes, nDirSend, dirSend, recvNodes, nDirRecv, dirRecv;
     long long sendCount = 0, recvCount = 0; // per field
     long long *d_sendSrc = nullptr, *d_recvDst = nullptr;
+    long long *d_phiSendSrc = nullptr, *d_phiRecvDst = nullptr; // scalar (phi) halo: slots of the phi array
+    double *d_phiSendBuf = nullptr, *d_phiRecvBuf = nullptr;
+    long long phiSendCount = 0, phiRecvCount = 0;
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;   // owned
     double *x_sendBuf = nullptr, *x_recvBuf = nullptr;   // caller-owned overrides (chimp_set_halo_buffers)
     double *sendBuf() const { return x_sendBuf ? x_sendBuf : d_sendBuf; }
@@ -136,8 +140,11 @@ struct chimp_lattice {
     cudaStream_t stream = nullptr, haloStream = nullptr;
     bool ownStream = false;
     cudaEvent_t evBoundary = nullptr, evHalo = nullptr, evStep = nullptr;
-    chimp_exchange_fn exchange = nullptr;
-    void *exchangeUser = nullptr;
+    chimp_exchange_fn exchange = nullptr, scalarExchange = nullptr;
+    void *exchangeUser = nullptr, *scalarExchangeUser = nullptr;
+    chimp_allreduce_fn allreduce = nullptr;
+    void *allreduceUser = nullptr;
+    std::vector<std::vector<long long>> hPhiSendSrc, hPhiRecvDst;
     long long steps = 0;
 };
 
@@ -218,7 +225,10 @@ int setupStreams(chimp_lattice *c)
 {
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->ownStream = true;
-    CUDA_OK(cudaStreamCreateWithFlags(&c->haloStream, cudaStreamNonBlocking));
+    // halo work (unpack kernels, the host's transport) must not queue behind the interior blocks
+    int prioLow = 0, prioHigh = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+    CUDA_OK(cudaStreamCreateWithPriority(&c->haloStream, cudaStreamNonBlocking, prioHigh));
     CUDA_OK(cudaEventCreateWithFlags(&c->evBoundary, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->evStep, cudaEventDisableTiming));
@@ -264,7 +274,8 @@ void launchMassChange(const chimp_lattice *c, const StepArgs &a, unsigned grid)
 
 int massChangePass(chimp_lattice *c, const StepArgs &a)
 {
-    if (!c->nbrs.empty()) return fail("mass-conservation source across ranks needs an all-reduce (not wired yet)");
+    if (!c->nbrs.empty() && !c->allreduce)
+        return fail("mass-conservation source across ranks needs chimp_set_allreduce_callback (std_one_phase/main.cpp:528)");
     const unsigned grid = (unsigned)((c->n + 255) / 256);
     if (!c->d_massPartial) {
         CUDA_OK(cudaMalloc(&c->d_massPartial, (size_t)grid * c->nLabels * sizeof(double)));
@@ -277,6 +288,13 @@ int massChangePass(chimp_lattice *c, const StepArgs &a)
     massFinalizeKernel<<<c->nLabels, 256, 0, c->stream>>>(c->d_massPartial, (int)grid, c->d_scale, c->d_mass, c->d_srcPerLabel);
     g_launches += 2;
     CUDA_OK(cudaGetLastError());
+    if (!c->nbrs.empty()) {
+        // MPI_Allreduce of massChangeLocal (main.cpp:528), then the source factors from the global sums
+        if (c->allreduce(c->allreduceUser, c->d_mass, c->nLabels, (void *)c->stream)) return fail("allreduce callback failed");
+        massFinalizeKernel<<<c->nLabels, 256, 0, c->stream>>>(c->d_mass, -1, c->d_scale, c->d_mass, c->d_srcPerLabel);
+        ++g_launches;
+        CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -425,6 +443,7 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
     const int nQ = li.nQ;
     const int nBulk = (int)c->bulk.size();
     const int32_t UNSET = -1;
+    const int32_t POISON = INT32_MIN; // a value whose orientation the kernels cannot express; an error only if an own node pulls it
     // symbolic slot contents: >= 0: (bulkIndex << 1) | reversed ; -1 unset ; <= -2: halo element -2-h
     std::vector<int32_t> sym((size_t)c->nNodes * nQ, UNSET);
     std::vector<int32_t> bulkIndex(c->nNodes, -1);
@@ -472,12 +491,12 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
     // 3. boundary copies in application order
     std::vector<uint32_t> pmaskB(nBulk, 0);
     auto orient = [&](int32_t code, int sq, int dq, int32_t &outCode) -> bool {
-        if (code == UNSET) { outCode = UNSET; return true; }
-        if (code <= -2) { outCode = code; return sq == dq; }
+        if (code == UNSET || code == POISON) { outCode = code; return true; }
+        if (code <= -2) { outCode = sq == dq ? code : POISON; return true; }
         const int actual = (code & 1) ? revDir(li, sq) : sq;
         if (actual == dq) outCode = code & ~1;
         else if (actual == revDir(li, dq)) outCode = code | 1;
-        else return false;
+        else outCode = POISON;
         return true;
     };
     for (const Op &op : c->ops) {
@@ -544,6 +563,8 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
             int32_t t;
             if (code == UNSET)
                 return fail("node %d direction %d has no upstream writer: geometry must be closed (walls with bounce back) or periodic", c->bulk[b], q);
+            if (code == POISON)
+                return fail("node %d direction %d receives a population through a boundary copy that changes its direction (unsupported link structure)", c->bulk[b], q);
             if (code <= -2) {
                 const auto &qh = haloQH[(size_t)(-2 - code)];
                 t = c->nPad + qh.second;
@@ -597,6 +618,16 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
         c->nGhost = g;
         const int zeroSlot = c->nPad + c->nSolid + c->nGhost;
         c->nPhi = zeroSlot + 1;
+        // MonLatMpi::communicateScalarField (LBmonlatmpi.h:181-205): field(nodesToSend) -> field(nodesReceived)
+        c->hPhiSendSrc.resize(c->nbrs.size());
+        c->hPhiRecvDst.resize(c->nbrs.size());
+        for (size_t k = 0; k < c->nbrs.size(); ++k) {
+            for (int node : c->nbrs[k].sendNodes) {
+                if (node < 0 || node >= c->nNodes || bulkIndex[node] < 0) return fail("scalar halo: node %d to send is not an own fluid node", node);
+                c->hPhiSendSrc[k].push_back(devOf[bulkIndex[node]]);
+            }
+            for (int node : c->nbrs[k].recvNodes) c->hPhiRecvDst[k].push_back(slotOf[node]);
+        }
         c->hPtable.assign((size_t)nQ * c->nPad, zeroSlot);
         for (int i = 0; i < nSlots; ++i) {
             const size_t row = (size_t)c->bulk[order[i]] * nQ;
@@ -650,6 +681,22 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
         }
     }
     if (c->nFields == 2) {
+        for (size_t k = 0; k < c->nbrs.size(); ++k) {
+            Neighbor &nb = c->nbrs[k];
+            const auto &src = c->hPhiSendSrc[k], &dst = c->hPhiRecvDst[k];
+            nb.phiSendCount = (long long)src.size();
+            nb.phiRecvCount = (long long)dst.size();
+            if (!src.empty()) {
+                CUDA_OK(cudaMalloc(&nb.d_phiSendSrc, src.size() * sizeof(long long)));
+                CUDA_OK(cudaMemcpy(nb.d_phiSendSrc, src.data(), src.size() * sizeof(long long), cudaMemcpyHostToDevice));
+                CUDA_OK(cudaMalloc(&nb.d_phiSendBuf, src.size() * sizeof(double)));
+            }
+            if (!dst.empty()) {
+                CUDA_OK(cudaMalloc(&nb.d_phiRecvDst, dst.size() * sizeof(long long)));
+                CUDA_OK(cudaMemcpy(nb.d_phiRecvDst, dst.data(), dst.size() * sizeof(long long), cudaMemcpyHostToDevice));
+                CUDA_OK(cudaMalloc(&nb.d_phiRecvBuf, dst.size() * sizeof(double)));
+            }
+        }
         CUDA_OK(cudaMalloc(&c->d_ptable, c->hPtable.size() * sizeof(int32_t)));
         CUDA_OK(cudaMemcpy(c->d_ptable, c->hPtable.data(), c->hPtable.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMalloc(&c->d_phi, (size_t)c->nPhi * sizeof(double)));
@@ -724,7 +771,10 @@ void chimp_destroy(chimp_lattice *c)
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
-    for (auto &nb : c->nbrs) { freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf); }
+    for (auto &nb : c->nbrs) {
+        freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf);
+        freeDev(nb.d_phiSendSrc); freeDev(nb.d_phiRecvDst); freeDev(nb.d_phiSendBuf); freeDev(nb.d_phiRecvBuf);
+    }
     if (c->evBoundary) cudaEventDestroy(c->evBoundary);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
     if (c->evStep) cudaEventDestroy(c->evStep);
@@ -924,9 +974,29 @@ int fillStepArgs(chimp_lattice *c, const chimp_single_params *p, StepArgs &a)
     return 0;
 }
 
+void packHalos(chimp_lattice *c, const double *X)
+{
+    const long long fieldStride = (long long)c->li.nQ * c->stride;
+    for (auto &nb : c->nbrs)
+        for (int f = 0; f < c->nFields && nb.sendCount; ++f) {
+            haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.sendBuf() + f * nb.sendCount, X + f * fieldStride, nb.d_sendSrc, (int)nb.sendCount);
+            ++g_launches;
+        }
+}
+
+void unpackHalos(chimp_lattice *c, double *X)
+{
+    const long long fieldStride = (long long)c->li.nQ * c->stride;
+    for (auto &nb : c->nbrs)
+        for (int f = 0; f < c->nFields && nb.recvCount; ++f) {
+            haloUnpackKernel<<<(unsigned)((nb.recvCount + 255) / 256), 256, 0, c->haloStream>>>(X + f * fieldStride, nb.recvBuf() + f * nb.recvCount, nb.d_recvDst, (int)nb.recvCount);
+            ++g_launches;
+        }
+}
+
 // first half of an iteration: collide + stream of all own nodes, halo-coupled nodes first, and
 // packing of the populations the neighbour ranks will pull
-int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom)
+int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom, bool callExchange)
 {
     StepArgs a;
     if (fillStepArgs(c, p, a)) return 1;
@@ -942,13 +1012,11 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom)
     a.begin = 0;
     a.end = c->nBoundary ? c->nBoundary : c->n;
     dispatchSingleLattice(c, a, p->collision, mom, c->stream);
-    for (auto &nb : c->nbrs)
-        if (nb.sendCount) {
-            haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.sendBuf(), foutBuf, nb.d_sendSrc, (int)nb.sendCount);
-            ++g_launches;
-        }
+    packHalos(c, foutBuf);
     CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
     CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+    // the transport is enqueued before the interior launch so that it is ahead of it in issue order
+    if (callExchange && c->exchange && c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
     if (c->nBoundary && c->nBoundary < c->n) {
         a.begin = c->nBoundary;
         a.end = c->n;
@@ -962,11 +1030,7 @@ int stepEnd(chimp_lattice *c)
 {
     double *fout = c->d_f[c->cur ^ 1];
     if (!c->nbrs.empty()) {
-        for (auto &nb : c->nbrs)
-            if (nb.recvCount) {
-                haloUnpackKernel<<<(unsigned)((nb.recvCount + 255) / 256), 256, 0, c->haloStream>>>(fout, nb.recvBuf(), nb.d_recvDst, (int)nb.recvCount);
-                ++g_launches;
-            }
+        unpackHalos(c, fout);
         CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
     }
@@ -981,7 +1045,7 @@ int chimp_step_begin(chimp_lattice *c, const chimp_single_params *p, int store_m
 {
     if (check(c, true)) return 1;
     CUDA_OK(cudaSetDevice(c->device));
-    if (stepBegin(c, p, store_moments != 0)) return 1;
+    if (stepBegin(c, p, store_moments != 0, false)) return 1;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1000,9 +1064,7 @@ int chimp_step_single(chimp_lattice *c, const chimp_single_params *p, int n_step
     if (check(c, true)) return 1;
     CUDA_OK(cudaSetDevice(c->device));
     for (int s = 0; s < n_steps; ++s) {
-        if (stepBegin(c, p, s == n_steps - 1)) return 1;
-        if (!c->nbrs.empty() && c->exchange && c->exchange(c->exchangeUser, (void *)c->haloStream))
-            return fail("exchange callback failed");
+        if (stepBegin(c, p, s == n_steps - 1, true)) return 1;
         if (stepEnd(c)) return 1;
     }
     CUDA_OK(cudaGetLastError());
@@ -1087,21 +1149,35 @@ int chimp_set_twophase_density(chimp_lattice *c, const double *rho2)
 extern "C++" {
 namespace {
 template <class L>
-void launchTwoPhase(chimp_lattice *c, const TwoPhaseArgs &a, const chimp_twophase_params *p, bool mom, unsigned gridAll)
+void launchPhaseMoments(chimp_lattice *c, const TwoPhaseArgs &a, unsigned gridAll)
 {
-    const bool rk = c->indexForm == CHIMP_INDEX_COMPACT;
-    if (rk) phaseMomentsKernel<L, IDX_COMPACT><<<gridAll, 256, 0, c->stream>>>(a);
+    if (c->indexForm == CHIMP_INDEX_COMPACT) phaseMomentsKernel<L, IDX_COMPACT><<<gridAll, 256, 0, c->stream>>>(a);
     else phaseMomentsKernel<L, IDX_TABLE><<<gridAll, 256, 0, c->stream>>>(a);
-    fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)gridAll, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, 1);
+    ++g_launches;
+}
+template <class L>
+void launchTwoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom)
+{
+    if (a.end <= a.begin) return;
     const unsigned grid = (unsigned)((a.end - a.begin + 255) / 256);
-    if (rk) {
+    if (c->indexForm == CHIMP_INDEX_COMPACT) {
         if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a);
         else twoPhaseCollideKernel<L, false, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a);
     } else {
         if (mom) twoPhaseCollideKernel<L, true, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a);
         else twoPhaseCollideKernel<L, false, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a);
     }
-    g_launches += 3;
+    ++g_launches;
+}
+void phaseMoments(chimp_lattice *c, const TwoPhaseArgs &a, unsigned gridAll)
+{
+    if (c->lattice == CHIMP_D2Q9) launchPhaseMoments<D2Q9>(c, a, gridAll);
+    else launchPhaseMoments<D3Q19>(c, a, gridAll);
+}
+void twoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom)
+{
+    if (c->lattice == CHIMP_D2Q9) launchTwoPhaseCollide<D2Q9>(c, a, mom);
+    else launchTwoPhaseCollide<D3Q19>(c, a, mom);
 }
 } // namespace
 } // extern "C++"
@@ -1113,7 +1189,9 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     if (c->nFields != 2) return fail("chimp_step_twophase needs a two-field lattice");
     if (c->lattice == CHIMP_D3Q27) return fail("D3Q27 has no colour-gradient weights B[] (not defined by the reference)");
     if (!c->densitySet) return fail("call chimp_set_twophase_density first (wall colour, main_TWOPHASE.cpp:173-181)");
-    if (!c->nbrs.empty()) return fail("N-rank twophase stepping is not wired yet");
+    const bool multi = !c->nbrs.empty();
+    if (multi && (!c->exchange || !c->scalarExchange || !c->allreduce))
+        return fail("N-rank twophase needs the exchange, scalar-exchange and allreduce callbacks");
     if (p->n_fluid_global <= 0) return fail("n_fluid_global must be positive");
     CUDA_OK(cudaSetDevice(c->device));
     TwoPhaseArgs a{};
@@ -1136,11 +1214,51 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     const unsigned gridAll = (unsigned)((c->n + 255) / 256);
     for (int s = 0; s < n_steps; ++s) {
         fillPlanes(c, a.pl);
-        a.begin = 0;
-        a.end = c->n;
+        double *const foutBuf = c->d_f[c->cur ^ 1];
         const bool mom = (s == n_steps - 1);
-        if (c->lattice == CHIMP_D2Q9) launchTwoPhase<D2Q9>(c, a, p, mom, gridAll);
-        else launchTwoPhase<D3Q19>(c, a, p, mom, gridAll);
+        // passes A + C (:238-246, :292-299): rho0, rho1, phi and the local x-momentum sum
+        phaseMoments(c, a, gridAll);
+        fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)gridAll, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, multi ? 0 : 1);
+        ++g_launches;
+        if (multi) {
+            // communciateScalarField(cgField) (:287) and MPI_Allreduce of the momentum sum (:299)
+            for (auto &nb : c->nbrs)
+                if (nb.phiSendCount) {
+                    haloPackKernel<<<(unsigned)((nb.phiSendCount + 255) / 256), 256, 0, c->stream>>>(nb.d_phiSendBuf, c->d_phi, nb.d_phiSendSrc, (int)nb.phiSendCount);
+                    ++g_launches;
+                }
+            if (c->scalarExchange(c->scalarExchangeUser, (void *)c->stream)) return fail("scalar exchange callback failed");
+            if (c->allreduce(c->allreduceUser, c->d_fluxSum, 1, (void *)c->stream)) return fail("allreduce callback failed");
+            for (auto &nb : c->nbrs)
+                if (nb.phiRecvCount) {
+                    haloUnpackKernel<<<(unsigned)((nb.phiRecvCount + 255) / 256), 256, 0, c->stream>>>(c->d_phi, nb.d_phiRecvBuf, nb.d_phiRecvDst, (int)nb.phiRecvCount);
+                    ++g_launches;
+                }
+            fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxSum, 1, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, 1);
+            ++g_launches;
+        }
+        // pass D (:312-376) + ghost exchange of both fields (:387-388)
+        if (!multi) {
+            a.begin = 0;
+            a.end = c->n;
+            twoPhaseCollide(c, a, mom);
+        } else {
+            a.begin = 0;
+            a.end = c->nBoundary ? c->nBoundary : c->n;
+            twoPhaseCollide(c, a, mom);
+            packHalos(c, foutBuf);
+            CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
+            CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+            if (c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
+            if (c->nBoundary && c->nBoundary < c->n) {
+                a.begin = c->nBoundary;
+                a.end = c->n;
+                twoPhaseCollide(c, a, mom);
+            }
+            unpackHalos(c, foutBuf);
+            CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
+            CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
+        }
         c->cur ^= 1;
         ++c->steps;
     }
@@ -1234,6 +1352,29 @@ int chimp_set_exchange_callback(chimp_lattice *c, chimp_exchange_fn fn, void *us
     c->exchangeUser = user;
     return 0;
 }
+int chimp_set_scalar_exchange_callback(chimp_lattice *c, chimp_exchange_fn fn, void *user)
+{
+    if (!c) return fail("null lattice handle");
+    c->scalarExchange = fn;
+    c->scalarExchangeUser = user;
+    return 0;
+}
+int chimp_set_allreduce_callback(chimp_lattice *c, chimp_allreduce_fn fn, void *user)
+{
+    if (!c) return fail("null lattice handle");
+    c->allreduce = fn;
+    c->allreduceUser = user;
+    return 0;
+}
+int chimp_scalar_neighbor_info(chimp_lattice *c, int k, long long *send_count, long long *recv_count)
+{
+    if (!c || k < 0 || k >= (int)c->nbrs.size()) return fail("bad neighbour index");
+    if (send_count) *send_count = c->nbrs[k].phiSendCount;
+    if (recv_count) *recv_count = c->nbrs[k].phiRecvCount;
+    return 0;
+}
+void *chimp_scalar_send_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].d_phiSendBuf : nullptr; }
+void *chimp_scalar_recv_buffer_dev(chimp_lattice *c, int k) { return (c && k >= 0 && k < (int)c->nbrs.size()) ? c->nbrs[k].d_phiRecvBuf : nullptr; }
 int chimp_set_stream(chimp_lattice *c, void *s)
 {
     if (!c) return fail("null lattice handle");

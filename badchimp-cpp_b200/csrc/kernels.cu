@@ -37,6 +37,10 @@ __global__ void massFinalizeKernel(const double *__restrict__ partial, int nBloc
 {
     __shared__ double sh[8];
     const int l = blockIdx.x;
+    if (nBlocks < 0) { // partial[] already holds the (all-reduced) sums
+        if (threadIdx.x == 0) src[l] = 0.9 * 2 * scale[l] * partial[l];
+        return;
+    }
     double v = 0.0;
     for (int b = threadIdx.x; b < nBlocks; b += blockDim.x) v += partial[(long long)l * nBlocks + b];
     const double s = blockSum256(v, sh);

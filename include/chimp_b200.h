@@ -165,6 +165,17 @@ int chimp_set_boundary_count(chimp_lattice *, int n_boundary);
 typedef int (*chimp_exchange_fn)(void *user, void *stream);
 /* called once per step after the boundary nodes were packed, on the halo stream */
 int chimp_set_exchange_callback(chimp_lattice *, chimp_exchange_fn fn, void *user);
+/* N-rank twophase / std_one_phase need two more transports, supplied the same way:
+ * - the scalar ghost exchange of cgField (MonLatMpi::communicateScalarField, LBmonlatmpi.h:181-205):
+ *   one double per ghost node, packed in chimp_scalar_send_buffer_dev(k) -> peer's chimp_scalar_recv_buffer_dev;
+ * - MPI_Allreduce(SUM) of `count` doubles in place at `dev` (momentum sum, main_TWOPHASE.cpp:299;
+ *   mass change per interior domain, std_one_phase/main.cpp:528). */
+typedef int (*chimp_allreduce_fn)(void *user, double *dev, int count, void *stream);
+int chimp_set_scalar_exchange_callback(chimp_lattice *, chimp_exchange_fn fn, void *user);
+int chimp_set_allreduce_callback(chimp_lattice *, chimp_allreduce_fn fn, void *user);
+int chimp_scalar_neighbor_info(chimp_lattice *, int k, long long *send_count, long long *recv_count);
+void *chimp_scalar_send_buffer_dev(chimp_lattice *, int k);
+void *chimp_scalar_recv_buffer_dev(chimp_lattice *, int k);
 /* use an externally owned stream (e.g. torch's current stream) for all launches */
 int chimp_set_stream(chimp_lattice *, void *cuda_stream);
 int chimp_synchronize(chimp_lattice *);

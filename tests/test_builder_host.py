@@ -142,3 +142,14 @@ def test_bad_arguments_are_reported():
     neigh[1, 0] = 7
     with pytest.raises(capi.ChimpError):
         capi.Lattice("D3Q19", neigh, [1, 2])          # neighbour out of range
+
+
+def test_two_rank_one_phase_tables_build():
+    """fluid-fluid swap links that touch ghost rows write values no own node ever pulls: the builder
+    must accept them (the 2-rank run itself is checked against the reference on the GPU)"""
+    g = helpers.Golden("onephase_trt_d3q19_p2")
+    lg, tabs = helpers.build_tables(g)
+    lats = build_engine_tables(g, lg, tabs, True)
+    for lat, t in zip(lats, tabs):
+        table, labels, pmask, info = lat.host_table()
+        assert info["n"] == len(t.bulk_nodes()) and (pmask != 0).any()

@@ -243,3 +243,140 @@ def test_twophase_vs_reference(name, index_form):
         assert abs(lat.last_flux_force() - fx) <= 1e-10 * abs(fx)
         if step == 1:
             assert np.array_equal(got_rho, ref_rho)
+
+
+class ThreadedRanks:
+    """N ranks as N engine contexts on one GPU, each driven by its own host thread, so that the
+    production code path (chimp_step_* with transport callbacks) runs unchanged; the callbacks
+    rendezvous on a barrier and move data with device copies -- a stand-in for NCCL / MPI."""
+
+    def __init__(self, lats):
+        import threading
+        self.lats = lats
+        self.n = len(lats)
+        self.barrier = threading.Barrier(self.n)
+        self.rt = C.CDLL("libcudart.so")
+        self.rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        self.rt.cudaStreamSynchronize.argtypes = [C.c_void_p]
+        self.shared = [None] * self.n
+        for r, lat in enumerate(lats):
+            lat.set_exchange_callback(self._exchange(r, False))
+            lat.set_scalar_exchange_callback(self._exchange(r, True))
+            lat.set_allreduce_callback(self._allreduce(r))
+
+    def _peer_index(self, other, r):
+        return [j for j in range(other.num_neighbors()) if other.neighbor_info(j)[0] == r][0]
+
+    def _exchange(self, r, scalar):
+        lat = self.lats[r]
+
+        def cb(stream):
+            assert self.rt.cudaStreamSynchronize(stream) == 0
+            self.barrier.wait()
+            for k in range(lat.num_neighbors()):
+                nr = lat.neighbor_info(k)[0]
+                other = self.lats[nr]
+                ko = self._peer_index(other, r)
+                if scalar:
+                    cnt = lat.scalar_neighbor_info(k)[1]
+                    src, dst = other.scalar_send_buffer_ptr(ko), lat.scalar_recv_buffer_ptr(k)
+                else:
+                    cnt = lat.neighbor_info(k)[2]
+                    src, dst = other.send_buffer_ptr(ko), lat.recv_buffer_ptr(k)
+                if cnt:
+                    assert self.rt.cudaMemcpy(dst, src, cnt * 8, 3) == 0
+            self.barrier.wait()
+        return cb
+
+    def _allreduce(self, r):
+        def cb(dev, count, stream):
+            assert self.rt.cudaStreamSynchronize(stream) == 0
+            mine = np.zeros(count)
+            assert self.rt.cudaMemcpy(mine.ctypes.data_as(C.c_void_p), dev, count * 8, 2) == 0
+            self.shared[r] = mine
+            self.barrier.wait()
+            total = self.shared[0].copy()
+            for k in range(1, self.n):      # rank order, like the oracle's MPI shim
+                total = total + self.shared[k]
+            self.barrier.wait()
+            assert self.rt.cudaMemcpy(dev, total.ctypes.data_as(C.c_void_p), count * 8, 1) == 0
+        return cb
+
+    def run(self, fn):
+        import threading
+        errors = []
+
+        def work(r):
+            try:
+                fn(r, self.lats[r])
+            except Exception as exc:  # pragma: no cover
+                errors.append((r, exc))
+                self.barrier.abort()
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(self.n)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+
+
+def test_twophase_two_ranks_vs_reference():
+    """2-rank colour-gradient run: scalar ghost exchange of phi between the passes, all-reduced flux
+    force, ghost exchange of both LbFields.  Tolerance as in the single-rank test (tree sums)."""
+    g = helpers.Golden("twophase_d3q19_p2")
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    setup = pkg.cases.two_phase_setup(lg, tabs, g.attr("rho0"), g.attr("rho1"), g.attr("wettability"))
+    lats = []
+    for r, t in enumerate(tabs):
+        lat = pkg.capi.Lattice.from_rank_tables(t, n_fields=2)
+        ss = t.send_side(tabs)
+        for k, nr in enumerate(t.neig_ranks):
+            lat.add_neighbor(nr, ss[k][0], ss[k][1], ss[k][2], t.recv_nodes[k], t.recv_ndir[k], t.recv_dirs[k])
+        lat.add_halfway_bb(*t.halfway_bb(t.bulk_nodes()))
+        lat.set_solid_boundary(setup[r]["solid_bnd"])
+        lat.finalize(1, True)
+        lat.set_twophase_density(setup[r]["rho"])
+        lat.upload(setup[r]["f0"])
+        lats.append(lat)
+    ranks = ThreadedRanks(lats)
+    a = g.args
+    n_global = sum(len(t.bulk_nodes()) for t in tabs)
+    done = 0
+    for step in [s for s in g.dump if s > 0]:
+        ranks.run(lambda r, lat: lat.step_twophase(step - done, a["tau2"][0], a["tau2"][1], a["sigma"], a["beta"], a["momx"],
+                                                   g.force(), n_global))
+        done = step
+        for r, (lat, t) in enumerate(zip(lats, tabs)):
+            bulk = t.bulk_nodes()
+            assert np.allclose(lat.download()[bulk], g.f(r, step, 2)[bulk], rtol=1e-12, atol=1e-300), "rank %d step %d" % (r, step)
+            assert np.allclose(lat.download_rho()[bulk], g.rec(r, "step%d.rho" % step).reshape(-1, 2)[bulk], rtol=1e-12, atol=0)
+            assert np.allclose(lat.download_phase_field()[bulk], g.rec(r, "step%d.cg" % step)[bulk], rtol=1e-10, atol=1e-14)
+            fx = float(g.rec(r, "step%d.forceX" % step)[0])
+            assert abs(lat.last_flux_force() - fx) <= 1e-10 * abs(fx)
+
+
+def test_one_phase_trt_two_ranks_vs_reference():
+    """2-rank std_one_phase loop with TRT, link boundaries and the all-reduced mass-conservation source"""
+    g = helpers.Golden("onephase_trt_d3q19_p2")
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    setup = helpers.one_phase_setup(g, lg, tabs)
+    lats = build_engine_tables(g, lg, tabs, True)
+    for r, lat in enumerate(lats):
+        lat.finalize(1, True)
+        s = setup[r]
+        lat.set_one_phase_attributes(s["force_on"], s["interior"], s["add_source"], s["scale"], g.args.get("rhow", 1.0))
+        lat.upload(s["f0"])
+    ranks = ThreadedRanks(lats)
+    trt = tuple(g.args["trt"])
+    done = 0
+    for step in [s for s in g.dump if s > 0]:
+        ranks.run(lambda r, lat: lat.step_single(step - done, force=g.force(), trt=trt))
+        done = step
+        for r, (lat, t) in enumerate(zip(lats, tabs)):
+            bulk = t.bulk_nodes()
+            assert np.allclose(lat.download()[bulk], g.f(r, step)[bulk], rtol=1e-12, atol=0), "rank %d step %d" % (r, step)
+            assert np.allclose(lat.download_rho()[bulk, 0], g.rec(r, "step%d.rho" % step)[bulk], rtol=1e-12, atol=0)
+            mass = lat.download_mass_change(len(setup[r]["scale"]))
+            assert np.allclose(mass, g.rec(r, "step%d.massChange" % step), rtol=1e-9, atol=1e-16)
