@@ -32,6 +32,15 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic_gb(lattice, index, n_nodes):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture (profiles/traffic.json)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["%s/%s" % (lattice, index)]
+        return t["dram_bytes_per_node"] * n_nodes / 1e9, t["source"]
+    except Exception:
+        return None, None
+
+
 def _clock_sampler(stop, out):
     q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -234,7 +243,10 @@ def run_b200(args):
                        "index_bytes_per_node": lat.index_bytes_per_node(), "setup_seconds": setup_s,
                        "mean_rho_error": mass_err},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_node": B_ALG[lattice]},
+                         "traffic": _traffic_gb(lattice, args.index, n)[0], "traffic_unit": "GB per launch (ncu dram read+write)",
+                         "traffic_source": _traffic_gb(lattice, args.index, n)[1],
+                         "algorithmic_gb_per_launch": B_ALG[lattice] * n / 1e9,
+                         "peak_source": peak_src, "bytes_per_node": B_ALG[lattice]},
             "e2e": e2e, "gpu_launches": int(launches2 - launches1), "clocks": _summarize_clocks(samples)}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port(pkg)

@@ -114,6 +114,8 @@ struct chimp_lattice {
     long long stride = 0;
     int indexForm = CHIMP_INDEX_TABLE;
     int32_t *d_table = nullptr, *d_ktable = nullptr, *d_label = nullptr;
+    int labelMin = 0, labelMax = -1;
+    bool labelsContiguous = false;
     uint32_t *d_delta = nullptr, *d_pmask = nullptr;
     int nWords = 0;
     int32_t *d_base = nullptr, *d_rows = nullptr;
@@ -743,6 +745,8 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
     c->nPad = n_pad;
     c->nHalo = n_halo;
     c->stride = (long long)n_pad + n_halo;
+    // the tables may still be in flight on the producer's stream (e.g. torch's): wait for the device once
+    CUDA_OK(cudaDeviceSynchronize());
     const size_t tb = (size_t)li.nQ * n_pad * sizeof(int32_t);
     CUDA_OK(cudaMalloc(&c->d_table, tb));
     CUDA_OK(cudaMemcpyAsync(c->d_table, table_dev, tb, cudaMemcpyDeviceToDevice, c->stream));
@@ -784,11 +788,21 @@ void chimp_destroy(chimp_lattice *c)
 }
 
 // ---- state transfer ---------------------------------------------------------------------
-static int maxLabelRows(chimp_lattice *c, long long &rows)
+// Own bulk rows of a host array span the label range [labelMin, labelMax] (vtklb numbers a rank's fluid
+// nodes 1..N first, so the range is normally exactly the bulk rows).  Transfers touch only that row
+// range; when it holds nothing but bulk rows (labelsContiguous) a download is a pure device->host copy,
+// otherwise the caller's rows are staged first so that non-bulk rows keep their content.
+static int labelRange(chimp_lattice *c)
 {
-    // the host arrays have grid.size() rows; without the host tables (device-table path) the
-    // largest label + 1 is the row count the caller must provide
-    rows = c->nNodes;
+    if (c->labelMax >= 0) return 0;
+    std::vector<int32_t> lab(c->n);
+    CUDA_OK(cudaMemcpy(lab.data(), c->d_label, (size_t)c->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int lo = INT32_MAX, hi = -1;
+    for (int v : lab) { lo = std::min(lo, v); hi = std::max(hi, v); }
+    if (c->n == 0) { lo = 0; hi = 0; }
+    c->labelMin = lo;
+    c->labelMax = hi;
+    c->labelsContiguous = (long long)hi - lo + 1 == c->n;
     return 0;
 }
 
@@ -797,18 +811,20 @@ int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
     if (check(c, true)) return 1;
     if (c->nNodes <= 0) return fail("upload in reference layout needs a lattice created from reference tables");
     CUDA_OK(cudaSetDevice(c->device));
-    long long rows;
-    maxLabelRows(c, rows);
-    const size_t bytes = (size_t)rows * c->nFields * c->li.nQ * sizeof(double);
+    if (labelRange(c)) return 1;
+    const size_t rowDoubles = (size_t)c->nFields * c->li.nQ;
+    const size_t rows = (size_t)(c->labelMax - c->labelMin + 1);
+    const size_t bytes = rows * rowDoubles * sizeof(double);
     double *d_aos = nullptr;
     CUDA_OK(cudaMalloc(&d_aos, bytes));
-    CUDA_OK(cudaMemcpyAsync(d_aos, f_aos, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_aos, f_aos + (size_t)c->labelMin * rowDoubles, bytes, cudaMemcpyHostToDevice, c->stream));
     const unsigned grid = (unsigned)((c->n + 255) / 256);
     double *X = c->d_f[c->cur];
+    const double *shifted = d_aos - (size_t)c->labelMin * rowDoubles; // kernels index rows by label
     switch (c->lattice) {
-    case CHIMP_D2Q9: scatterStateKernel<D2Q9><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
-    case CHIMP_D3Q19: scatterStateKernel<D3Q19><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
-    case CHIMP_D3Q27: scatterStateKernel<D3Q27><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D2Q9: scatterStateKernel<D2Q9><<<grid, 256, 0, c->stream>>>(shifted, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q19: scatterStateKernel<D3Q19><<<grid, 256, 0, c->stream>>>(shifted, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q27: scatterStateKernel<D3Q27><<<grid, 256, 0, c->stream>>>(shifted, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
     }
     ++g_launches;
     CUDA_OK(cudaGetLastError());
@@ -822,23 +838,25 @@ int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
     if (check(c, true)) return 1;
     if (c->nNodes <= 0) return fail("download in reference layout needs a lattice created from reference tables");
     CUDA_OK(cudaSetDevice(c->device));
-    long long rows;
-    maxLabelRows(c, rows);
-    const size_t bytes = (size_t)rows * c->nFields * c->li.nQ * sizeof(double);
+    if (labelRange(c)) return 1;
+    const size_t rowDoubles = (size_t)c->nFields * c->li.nQ;
+    const size_t rows = (size_t)(c->labelMax - c->labelMin + 1);
+    const size_t bytes = rows * rowDoubles * sizeof(double);
+    double *host = f_aos + (size_t)c->labelMin * rowDoubles;
     double *d_aos = nullptr;
     CUDA_OK(cudaMalloc(&d_aos, bytes));
-    // rows that are not own bulk nodes keep the caller's content
-    CUDA_OK(cudaMemcpyAsync(d_aos, f_aos, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (!c->labelsContiguous) CUDA_OK(cudaMemcpyAsync(d_aos, host, bytes, cudaMemcpyHostToDevice, c->stream));
     const unsigned grid = (unsigned)((c->n + 255) / 256);
     const double *X = c->d_f[c->cur];
+    double *shifted = d_aos - (size_t)c->labelMin * rowDoubles;
     switch (c->lattice) {
-    case CHIMP_D2Q9: gatherStateKernel<D2Q9><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
-    case CHIMP_D3Q19: gatherStateKernel<D3Q19><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
-    case CHIMP_D3Q27: gatherStateKernel<D3Q27><<<grid, 256, 0, c->stream>>>(d_aos, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D2Q9: gatherStateKernel<D2Q9><<<grid, 256, 0, c->stream>>>(shifted, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q19: gatherStateKernel<D3Q19><<<grid, 256, 0, c->stream>>>(shifted, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q27: gatherStateKernel<D3Q27><<<grid, 256, 0, c->stream>>>(shifted, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
     }
     ++g_launches;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpyAsync(f_aos, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(host, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     cudaFree(d_aos);
     return 0;
@@ -847,15 +865,20 @@ int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
 static int downloadPlanes(chimp_lattice *c, double *host, const double *planes, int nComp, int aosStride, int aosOffset)
 {
     CUDA_OK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)c->nNodes * aosStride * sizeof(double);
+    if (labelRange(c)) return 1;
+    const size_t rows = (size_t)(c->labelMax - c->labelMin + 1);
+    const size_t bytes = rows * aosStride * sizeof(double);
+    double *hostRows = host + (size_t)c->labelMin * aosStride;
     double *d_aos = nullptr;
     CUDA_OK(cudaMalloc(&d_aos, bytes));
-    CUDA_OK(cudaMemcpyAsync(d_aos, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    // a full overwrite of the row range needs no staging; partial rows (aosStride > nComp) or
+    // non-bulk rows inside the range keep the caller's content
+    if (!c->labelsContiguous || nComp != aosStride) CUDA_OK(cudaMemcpyAsync(d_aos, hostRows, bytes, cudaMemcpyHostToDevice, c->stream));
     const unsigned grid = (unsigned)((c->n + 255) / 256);
-    planesToAosKernel<<<grid, 256, 0, c->stream>>>(d_aos, planes, c->d_label, c->n, c->nPad, nComp, aosStride, aosOffset);
+    planesToAosKernel<<<grid, 256, 0, c->stream>>>(d_aos - (size_t)c->labelMin * aosStride, planes, c->d_label, c->n, c->nPad, nComp, aosStride, aosOffset);
     ++g_launches;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpyAsync(host, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(hostRows, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     cudaFree(d_aos);
     return 0;

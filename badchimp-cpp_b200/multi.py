@@ -158,7 +158,8 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
                            "halo_bytes_per_step_per_gpu": 8.0 * (sum(lat._ring.counts[0::2])),
                            "setup_seconds": setup_s, "mean_rho_error": mass_err},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "per": "GPU (mean)"},
+                             "traffic": B._traffic_gb(lattice, args.index, n_total / world)[0], "traffic_unit": "GB per launch per GPU (ncu dram read+write)",
+                             "peak_source": peak_src, "per": "GPU (mean)"},
                 "e2e": e2e, "gpu_launches": int(l2 - l1), "clocks": B._summarize_clocks(samples)}
         print(json.dumps(line), flush=True)
     dist.barrier()
