@@ -542,6 +542,7 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
         for (int b = 0; b < nBulk; ++b) order.push_back(b);
     }
     const int nSlots = (int)order.size();
+    if (nSlots == 0) return fail("the lattice has no own fluid nodes (empty bulk list)");
     for (int i = 0; i < nSlots; ++i) if (order[i] >= 0) devOf[order[i]] = i;
     c->n = nSlots;
     // the first launch covers whole warp tiles: it may include a few uncoupled nodes

@@ -76,7 +76,24 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
     device = torch.device("cuda", local)
     t_setup = time.perf_counter()
     gshape = (size, size, size * world)
-    ext = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, rank * size - 1, (rank + 1) * size + 1)
+    z0, z1 = rank * size, (rank + 1) * size
+    ext = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, z0 - 1, z1 + 1)
+    if getattr(args, "balance", True):
+        # cut planes chosen so that every rank owns the same number of fluid nodes (the step time is the
+        # maximum over ranks; equal-thickness slabs of a random pack differ by several per cent)
+        layers = torch.from_numpy(ext[:, :, 1:-1].reshape(-1, size).sum(axis=0).astype(np.int64)).to(device)
+        all_layers = [torch.zeros_like(layers) for _ in range(world)]
+        dist.all_gather(all_layers, layers)
+        cum = torch.cumsum(torch.cat(all_layers), 0).cpu().numpy()
+        targets = cum[-1] * np.arange(1, world) / world
+        cuts = [0]
+        for t in targets:
+            k = int(np.searchsorted(cum, t))          # cum[k-1] < t <= cum[k]
+            below = cum[k - 1] if k > 0 else 0
+            cuts.append(k if (t - below) < (cum[k] - t) else k + 1)
+        cuts.append(size * world)
+        z0, z1 = cuts[rank], cuts[rank + 1]
+        ext = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, z0 - 1, z1 + 1)
     slab = ingest.build_slab_tables(torch.from_numpy(ext).to(device).bool(), lattice, boundary_first=True)
     index_form = capi.INDEX_COMPACT if args.index == "compact" else capi.INDEX_TABLE
     lat = capi.lattice_from_device_table(lattice, slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
@@ -109,6 +126,10 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
     dist.barrier()
     torch.cuda.synchronize()
     ms_max = total(ms, dist.ReduceOp.MAX)
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device=device)
+    per_rank[rank] = torch.tensor([float(n), float(ms) / args.steps, float(z1 - z0)], dtype=torch.float64, device=device)
+    dist.all_reduce(per_rank)
+    per_rank = per_rank.cpu().numpy()
     if rank == 0:
         t_extra = time.perf_counter()
         while len(samples) < 6 and time.perf_counter() - t_extra < 2.0:
@@ -156,6 +177,9 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
                            "fluid_nodes": n_total, "index_form": args.index, "parallelism": "z-slab x%d, NCCL send/recv halos overlapped with interior nodes" % world,
                            "l2_policy": "state per GPU 2 x %.1f GB >> 126 MB L2" % (n * 152 / 1e9),
                            "halo_bytes_per_step_per_gpu": 8.0 * (sum(lat._ring.counts[0::2])),
+                           "slabs": "balanced by fluid-node count" if getattr(args, "balance", True) else "equal thickness",
+                           "nodes_per_rank": [int(x) for x in per_rank[:, 0]], "ms_per_step_per_rank": [round(float(x), 4) for x in per_rank[:, 1]],
+                           "slab_thickness_per_rank": [int(x) for x in per_rank[:, 2]],
                            "setup_seconds": setup_s, "mean_rho_error": mass_err},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": B._traffic_gb(lattice, args.index, n_total / world)[0], "traffic_unit": "GB per launch per GPU (ncu dram read+write)",

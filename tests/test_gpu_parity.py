@@ -380,3 +380,53 @@ def test_one_phase_trt_two_ranks_vs_reference():
             assert np.allclose(lat.download_rho()[bulk, 0], g.rec(r, "step%d.rho" % step)[bulk], rtol=1e-12, atol=0)
             mass = lat.download_mass_change(len(setup[r]["scale"]))
             assert np.allclose(mass, g.rec(r, "step%d.massChange" % step), rtol=1e-9, atol=1e-16)
+
+
+@pytest.mark.parametrize("shape,lattice,periodic", [((1, 1, 1), "D3Q19", "xyz"), ((3, 1, 2), "D3Q27", "xyz"), ((5, 3), "D2Q9", "xy"),
+                                                    ((33, 1, 1), "D3Q19", "xyz")])
+def test_tiny_and_ragged_lattices(shape, lattice, periodic):
+    """edge cases: a single periodic node (every neighbour is the node itself), node counts that are
+    not a multiple of the 32-node tile, one-node-thick domains"""
+    pkg = helpers.load_package()
+    port = helpers.oracle_port()
+    geo = np.ones(shape, dtype=int)
+    lg = pkg.geometry.LatticeGeometry(geo, lattice, periodic)
+    t = lg.all_ranks()[0]
+    rng = np.random.default_rng(1)
+    f0, _ = pkg.cases.std_case_initial_state(t, 1.0 + 0.1 * rng.random(shape))
+    bb = t.halfway_bb(t.fluid_bnd_nodes())
+    bulk = t.bulk_nodes()
+    for form in (0, 1):
+        lat = pkg.capi.Lattice.from_rank_tables(t)
+        lat.add_halfway_bb(*bb)
+        lat.finalize(form)
+        lat.upload(f0)
+        lat.step_single(7, tau=0.9, force=(1e-5, 2e-5, -1e-5)[: lg.nd])
+        ref = port.PortRank(pkg.geometry.LATTICE_ID[lattice], t.neigh, bulk, 1, bb)
+        ref.f[:] = f0
+        ref.step_std_case(7, tau=0.9, force=(1e-5, 2e-5, -1e-5)[: lg.nd])
+        assert np.array_equal(lat.download()[bulk], ref.f[bulk])
+        lat.close()
+
+
+def test_lattice_without_fluid_nodes_is_rejected():
+    pkg = helpers.load_package()
+    geo = np.zeros((4, 4, 4), dtype=int)
+    geo[0, 0, 0] = 1
+    t = pkg.geometry.LatticeGeometry(geo, "D3Q19", "xyz").all_ranks()[0]
+    with pytest.raises(pkg.capi.ChimpError):
+        pkg.capi.Lattice("D3Q19", t.neigh, np.zeros(0, dtype=np.int32)).finalize()
+
+
+def test_step_argument_errors():
+    pkg = helpers.load_package()
+    g = helpers.Golden("std_d2q9_channel")
+    lg, tabs = helpers.build_tables(g)
+    lat = build_engine_tables(g, lg, tabs, False)[0]
+    with pytest.raises(pkg.capi.ChimpError):
+        lat.step_single(1)                       # not finalized
+    lat.finalize(1)
+    with pytest.raises(pkg.capi.ChimpError):
+        lat.step_twophase(1, 1.0, 1.0, 0.01, 1.0, 1e-5, (0, 0, 0), 10)   # one-field lattice
+    with pytest.raises(pkg.capi.ChimpError):
+        lat.finalize(1)                          # twice
