@@ -54,7 +54,7 @@ SYMBOLS = [
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
-    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
+    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
 ]
 
 
@@ -283,6 +283,12 @@ class Lattice:
 
     def halo_stream(self):
         return lib().chimp_halo_stream(self.h)
+
+    def init_equilibrium_dev(self, rho_ptr):
+        _check(lib().chimp_init_equilibrium_dev(self.h, C.c_void_p(rho_ptr)))
+
+    def set_phi_table_dev(self, ptable_ptr, n_extra, phi_extra_ptr):
+        _check(lib().chimp_set_phi_table_dev(self.h, C.c_void_p(ptable_ptr), C.c_int(n_extra), C.c_void_p(phi_extra_ptr)))
 
     def init_uniform(self, rho=1.0):
         _check(lib().chimp_init_uniform(self.h, C.c_double(rho)))

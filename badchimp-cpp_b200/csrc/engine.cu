@@ -768,7 +768,7 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
 void chimp_destroy(chimp_lattice *c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
+    if (c->device >= 0) cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     freeDev(c->d_table); freeDev(c->d_ktable); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
@@ -1003,7 +1003,7 @@ void packHalos(chimp_lattice *c, const double *X)
     const long long fieldStride = (long long)c->li.nQ * c->stride;
     for (auto &nb : c->nbrs)
         for (int f = 0; f < c->nFields && nb.sendCount; ++f) {
-            haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->stream>>>(nb.sendBuf() + f * nb.sendCount, X + f * fieldStride, nb.d_sendSrc, (int)nb.sendCount);
+            haloPackKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->haloStream>>>(nb.sendBuf() + f * nb.sendCount, X + f * fieldStride, nb.d_sendSrc, (int)nb.sendCount);
             ++g_launches;
         }
 }
@@ -1033,12 +1033,15 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom, bool cal
         dispatchSingleLattice(c, a, p->collision, mom, c->stream);
         return 0;
     }
+    // The halo-coupled nodes (first slots) are stepped and packed on the high-priority halo stream while
+    // the interior nodes run on the main stream: both read the old buffer and write disjoint slots of the
+    // new one.  evStep orders the halo stream behind everything the main stream did up to here.
+    CUDA_OK(cudaEventRecord(c->evStep, c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evStep, 0));
     a.begin = 0;
     a.end = c->nBoundary ? c->nBoundary : c->n;
-    dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+    dispatchSingleLattice(c, a, p->collision, mom, c->haloStream);
     packHalos(c, foutBuf);
-    CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
-    CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
     // the transport is enqueued before the interior launch so that it is ahead of it in issue order
     if (callExchange && c->exchange && c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
     if (c->nBoundary && c->nBoundary < c->n) {
@@ -1128,6 +1131,51 @@ int chimp_init_uniform(chimp_lattice *c, double rho)
         }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int chimp_init_equilibrium_dev(chimp_lattice *c, const double *rho_dev)
+{
+    if (check(c, true)) return 1;
+    if (!rho_dev) return fail("rho_dev is null");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaDeviceSynchronize()); // rho may come from another stream
+    const unsigned grid = (unsigned)((c->n + 255) / 256);
+    double *X = c->d_f[c->cur];
+    switch (c->lattice) {
+    case CHIMP_D2Q9: initEquilibriumKernel<D2Q9><<<grid, 256, 0, c->stream>>>(rho_dev, X, c->d_table, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q19: initEquilibriumKernel<D3Q19><<<grid, 256, 0, c->stream>>>(rho_dev, X, c->d_table, c->n, c->nPad, c->stride, c->nFields); break;
+    case CHIMP_D3Q27: initEquilibriumKernel<D3Q27><<<grid, 256, 0, c->stream>>>(rho_dev, X, c->d_table, c->n, c->nPad, c->stride, c->nFields); break;
+    }
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int chimp_set_phi_table_dev(chimp_lattice *c, const int32_t *ptable_dev, int n_extra, const double *phi_extra_dev)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2) return fail("needs a two-field lattice");
+    if (!ptable_dev || n_extra < 0 || (n_extra > 0 && !phi_extra_dev)) return fail("bad phi table arguments");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
+    const size_t tb = (size_t)c->li.nQ * c->nPad * sizeof(int32_t);
+    CUDA_OK(cudaMalloc(&c->d_ptable, tb));
+    CUDA_OK(cudaMemcpy(c->d_ptable, ptable_dev, tb, cudaMemcpyDeviceToDevice));
+    c->nSolid = n_extra;
+    c->nGhost = 0;
+    c->nPhi = c->nPad + n_extra + 1;
+    CUDA_OK(cudaMalloc(&c->d_phi, (size_t)c->nPhi * sizeof(double)));
+    CUDA_OK(cudaMemset(c->d_phi, 0, (size_t)c->nPhi * sizeof(double)));
+    if (n_extra) CUDA_OK(cudaMemcpy(c->d_phi + c->nPad, phi_extra_dev, (size_t)n_extra * sizeof(double), cudaMemcpyDeviceToDevice));
+    const int nBlocks = (c->n + 255) / 256;
+    CUDA_OK(cudaMalloc(&c->d_fluxPartial, (size_t)std::max(nBlocks, 1) * sizeof(double)));
+    CUDA_OK(cudaMalloc(&c->d_fluxSum, sizeof(double)));
+    CUDA_OK(cudaMalloc(&c->d_forceX, sizeof(double)));
+    CUDA_OK(cudaMemset(c->d_forceX, 0, sizeof(double)));
+    c->densitySet = true;
     return 0;
 }
 
@@ -1270,9 +1318,9 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
             a.begin = 0;
             a.end = c->nBoundary ? c->nBoundary : c->n;
             twoPhaseCollide(c, a, mom);
-            packHalos(c, foutBuf);
             CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
             CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+            packHalos(c, foutBuf);
             if (c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
             if (c->nBoundary && c->nBoundary < c->n) {
                 a.begin = c->nBoundary;

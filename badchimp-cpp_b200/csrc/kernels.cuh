@@ -463,6 +463,27 @@ __global__ void scatterStateKernel(const double *__restrict__ aos, double *X, co
     }
 }
 
+// state f_{s,q}(i) = w_q * rho_s(i) (initiateLbField with u = 0, LBinitiatefield.h:52-56), written through the
+// pull table so that the first step pulls exactly these values; rho is [nFields][n] in device node order
+template <class L>
+__global__ void initEquilibriumKernel(const double *__restrict__ rho, double *X, const int32_t *__restrict__ table, int n,
+                                      int nPad, long long stride, int nFields)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int fl = 0; fl < nFields; ++fl) {
+        double *Xf = X + (long long)fl * L::nQ * stride;
+        const double r = rho[(long long)fl * n + i];
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) {
+            const double v = L::w(q) * r * 1.0;
+            const int s = table[(long long)q * nPad + i];
+            if (s >= 0) Xf[(long long)q * stride + s] = v;
+            else Xf[(long long)reverseDir<L>(q) * stride + i] = v;
+        }
+    }
+}
+
 template <class L>
 __global__ void gatherStateKernel(double *aos, const double *__restrict__ X, const int32_t *__restrict__ table,
                                   const int32_t *__restrict__ label, int n, int nPad, long long stride, int nFields)

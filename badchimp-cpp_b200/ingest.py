@@ -179,3 +179,43 @@ def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: boo
     faces = {k: (cat(v[0]), cat(v[1])) for k, v in faces.items()}
     return dict(table=table, labels=labels, n=n, n_pad=n_pad, n_halo=n_halo, n_boundary=n_boundary, faces=faces,
                 stride=stride)
+
+
+def build_phi_table(fluid: torch.Tensor, wall_phi: torch.Tensor, lattice: str, periodic: str = "xyz"):
+    """Colour-gradient support tables of a single-rank two-phase lattice (twophase/main_TWOPHASE.cpp):
+    ptable[q][i] = phi slot of neighbor(q, n_i) -- own fluid node -> its slot, solid cell next to a
+    fluid cell (the reference's solid boundary nodes, LBgeometry.h:37-45) -> n_pad + k, anything else ->
+    the zero slot n_pad + n_extra -- and the wall colours phi_extra[k] = wall_phi at those solid cells.
+    Non-periodic axes are closed (outside = zero slot)."""
+    basis = G.BASIS[lattice]
+    nq, nd = basis.shape
+    fluid = fluid.bool()
+    dev = fluid.device
+    flat = fluid.reshape(-1)
+    n = int(flat.sum().item())
+    n_pad = ((n + 31) // 32) * 32
+    dims = tuple(range(nd))
+    near = torch.zeros_like(fluid)
+    for q in range(nq - 1):
+        c = [int(x) for x in basis[q]]
+        near |= torch.roll(fluid, shifts=c, dims=dims)   # cell has a fluid neighbour
+    wall = near & ~fluid
+    n_extra = int(wall.sum().item())
+    slot = torch.full(fluid.shape, n_pad + n_extra, dtype=torch.int32, device=dev)
+    slot[fluid] = torch.arange(n, dtype=torch.int32, device=dev)
+    slot[wall] = n_pad + torch.arange(n_extra, dtype=torch.int32, device=dev)
+    own = torch.nonzero(flat).reshape(-1)
+    ptable = torch.full((nq, n_pad), n_pad + n_extra, dtype=torch.int32, device=dev)
+    for q in range(nq):
+        c = [-int(x) for x in basis[q]]                   # value at pos + c_q
+        nb = torch.roll(slot, shifts=c, dims=dims) if any(c) else slot
+        if any(c):
+            for ax, name in enumerate("xyz"[:nd]):
+                if name in periodic.lower() or c[ax] == 0:
+                    continue
+                sl = [slice(None)] * nd
+                sl[ax] = 0 if c[ax] > 0 else -1
+                nb = nb.clone()
+                nb[tuple(sl)] = n_pad + n_extra
+        ptable[q, :n] = nb.reshape(-1)[own]
+    return ptable, n_extra, wall_phi.to(dev).double()[wall].contiguous()

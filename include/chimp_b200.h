@@ -130,6 +130,14 @@ int chimp_step_timed(chimp_lattice *, const chimp_single_params *, int n_steps, 
 /* state f_q(n) = w_q * rho for every own node (std_case/main.cpp:92-96 with constant rho);
  * works for lattices created from device tables, where no reference-layout upload exists */
 int chimp_init_uniform(chimp_lattice *, double rho);
+/* structured-ingest lattices: state f_{s,q}(i) = w_q * rho_s(i) (initiateLbField with u = 0,
+ * LBinitiatefield.h:33-57) from a device array rho [n_fields][n_own] in device node order */
+int chimp_init_equilibrium_dev(chimp_lattice *, const double *rho_dev);
+/* structured-ingest two-field lattices: the phi slot of neighbor(q, n) for every own node
+ * (int32 [nQ][n_pad]: own slot, n_pad + k for extra slot k, n_pad + n_extra for "always 0") and the constant
+ * colour of the n_extra wall slots (main_TWOPHASE.cpp:280-284); replaces chimp_set_solid_boundary +
+ * chimp_set_twophase_density of the reference-table path */
+int chimp_set_phi_table_dev(chimp_lattice *, const int32_t *ptable_dev, int n_extra, const double *phi_extra_dev);
 /* rho [n_own] and vel [nD][n_own] of the last step, in device node order */
 int chimp_download_moments_device_order(chimp_lattice *, double *rho, double *vel);
 

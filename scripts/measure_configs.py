@@ -62,34 +62,32 @@ def main():
         single("D3Q19 TRT sphere pack 512^3 (configs[2] collision)", torch.from_numpy(geo).cuda().bool(), "D3Q19", "xyz", 304.0,
                trt=(0.8, 1.125))
     if "twophase" in what:
-        # colour gradient, 2 fields, 384^3 pack: host tables would need the reference-table path, so the
-        # two-field lattice is created through the generic builder at a size it handles quickly (128^3)
-        size = int(os.environ.get("TWOPHASE_SIZE", "128"))
-        geo = pkg.geometry.sphere_pack((size,) * 3, size / 8.0, 0.35, 1234).astype(int)
-        t0 = time.time()
-        lg = pkg.geometry.LatticeGeometry(geo, "D3Q19", "xyz")
-        t = lg.all_ranks()[0]
-        x = np.arange(size)[:, None, None] * np.ones(geo.shape)
-        rho0 = (x < size / 2).astype(float)
-        setup = pkg.cases.two_phase_setup(lg, [t], rho0, 1.0 - rho0, 0.5 * (geo == 0))[0]
-        lat = capi.Lattice.from_rank_tables(t, n_fields=2)
-        lat.add_halfway_bb(*t.halfway_bb(t.bulk_nodes()))
-        lat.set_solid_boundary(setup["solid_bnd"])
-        lat.finalize(capi.INDEX_COMPACT)
-        lat.set_twophase_density(setup["rho"])
-        lat.upload(setup["f0"])
-        n = len(t.bulk_nodes())
+        # colour gradient, 2 LbFields, sphere pack 384^3 (configs[3] geometry on one GPU), device-side ingest
+        size = int(os.environ.get("TWOPHASE_SIZE", "384"))
+        geo = pkg.geometry.sphere_pack((size,) * 3, size / 8.0, 0.35, 1234)
+        fluid = torch.from_numpy(geo).cuda().bool()
+        table, labels, n, n_pad = ingest.build_pull_table(fluid, "D3Q19", "xyz")
+        lat = capi.lattice_from_device_table("D3Q19", n, n_pad, 0, table.data_ptr(), labels.data_ptr(), 2, capi.INDEX_COMPACT)
+        del table, labels
+        wall_phi = torch.zeros(geo.shape, dtype=torch.float64)          # wettability 0.5: rho0 = rho1 at the wall
+        ptable, n_extra, phi_extra = ingest.build_phi_table(fluid, wall_phi, "D3Q19", "xyz")
+        lat.set_phi_table_dev(ptable.data_ptr(), n_extra, phi_extra.data_ptr())
+        x = torch.arange(size, device="cuda")[:, None, None].expand(size, size, size)
+        r0 = (x < size // 2).double()[fluid]
+        rho_dev = torch.stack([r0, 1.0 - r0]).contiguous()
+        lat.init_equilibrium_dev(rho_dev.data_ptr())
+        del ptable, fluid, rho_dev
+        torch.cuda.empty_cache()
         args = (1.0, 1.0, 0.01, 1.0, 1e-5, (0, 0, 0), n)
         lat.step_twophase(5, *args)
         lat.synchronize()
-        torch.cuda.synchronize()
-        setup_s = time.time() - t0
         t1 = time.perf_counter()
-        lat.step_twophase(100, *args)
+        lat.step_twophase(60, *args)
         lat.synchronize()
         ms = (time.perf_counter() - t1) * 1e3
-        report("twophase colour gradient D3Q19 sphere pack %d^3 (configs[3] physics)" % size, n, ms, 100, 624.0,
-               "host-clock timing of 100 steps (3 launches per step); setup %.1f s" % setup_s)
+        rho, _ = lat.download_moments_device_order()
+        report("twophase colour gradient D3Q19 sphere pack %d^3 (configs[3] physics, one GPU)" % size, n, ms, 60, 624.0,
+               "host-clock timing of 60 steps (3 launches per step); flux force %.3e" % lat.last_flux_force())
 
 
 if __name__ == "__main__":

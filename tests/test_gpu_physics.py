@@ -83,3 +83,49 @@ def test_mass_conservation_and_index_form_agreement_at_larger_size(lattice):
     assert np.array_equal(rho_a, rho_b) and np.array_equal(vel_a, vel_b)
     assert abs(rho_a.sum() / len(rho_a) - 1.0) < 1e-12
     assert vel_a[0].mean() > 0
+
+
+def test_twophase_structured_ingest_equals_reference_table_path():
+    """two-field lattice built by the device-side ingest (pull table + phi table + equilibrium init)
+    gives bit-identical populations to the one built from the reference's tables"""
+    import importlib
+    import torch
+    pkg = helpers.load_package()
+    ingest = importlib.import_module("badchimp_cpp_b200.ingest")
+    shape = (26, 22, 24)
+    geo = pkg.geometry.sphere_pack(shape, 5.0, 0.5, 13).astype(int)
+    x = np.arange(shape[0])[:, None, None] * np.ones(shape)
+    rho0 = (x < shape[0] / 2).astype(float)
+    wet = 0.25 * (geo == 0)
+    lg = pkg.geometry.LatticeGeometry(geo, "D3Q19", "xyz")
+    t = lg.all_ranks()[0]
+    setup = pkg.cases.two_phase_setup(lg, [t], rho0, 1.0 - rho0, wet)[0]
+    a = pkg.capi.Lattice.from_rank_tables(t, n_fields=2)
+    a.add_halfway_bb(*t.halfway_bb(t.bulk_nodes()))
+    a.set_solid_boundary(setup["solid_bnd"])
+    a.finalize(pkg.capi.INDEX_COMPACT)
+    a.set_twophase_density(setup["rho"])
+    a.upload(setup["f0"])
+    n = len(t.bulk_nodes())
+    args = (1.0, 0.8, 0.01, 1.0, 1e-5, (0, 1e-7, 0), n)
+    a.step_twophase(20, *args)
+    fa = a.download()[t.bulk_nodes()]
+    # device path
+    fluid = torch.from_numpy(geo > 0).cuda()
+    table, labels, nd_, n_pad = ingest.build_pull_table(fluid, "D3Q19", "xyz")
+    assert nd_ == n
+    b = pkg.capi.lattice_from_device_table("D3Q19", n, n_pad, 0, table.data_ptr(), labels.data_ptr(), 2, pkg.capi.INDEX_COMPACT)
+    w32 = torch.from_numpy(wet.astype(np.float32))
+    wall_phi = ((w32 - (1.0 - w32)) .double() / (w32.double() + (1.0 - w32).double()))
+    # the reference computes (rho0 - rho1)/(rho0 + rho1) from float32-parsed wall densities (main_TWOPHASE.cpp:173-181, 280-284)
+    r0 = w32.double()
+    r1 = (torch.tensor(1.0, dtype=torch.float32) - w32).double()
+    wall_phi = (r0 - r1) / (r0 + r1)
+    ptable, n_extra, phi_extra = ingest.build_phi_table(fluid, wall_phi, "D3Q19", "xyz")
+    b.set_phi_table_dev(ptable.data_ptr(), n_extra, phi_extra.data_ptr())
+    rho_dev = torch.stack([torch.from_numpy(rho0)[torch.from_numpy(geo > 0)], torch.from_numpy(1.0 - rho0)[torch.from_numpy(geo > 0)]]).cuda().contiguous()
+    b.init_equilibrium_dev(rho_dev.data_ptr())
+    b.step_twophase(20, *args)
+    b.n_nodes = n + 1
+    fb = b.download()[1:]
+    assert np.array_equal(fa, fb)
