@@ -1231,13 +1231,13 @@ template <class L>
 void launchTwoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom)
 {
     if (a.end <= a.begin) return;
-    const unsigned grid = (unsigned)((a.end - a.begin + 255) / 256);
+    const unsigned grid = (unsigned)((a.end - a.begin + CHIMP_TP_BLOCK - 1) / CHIMP_TP_BLOCK);
     if (c->indexForm == CHIMP_INDEX_COMPACT) {
-        if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a);
-        else twoPhaseCollideKernel<L, false, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a);
+        if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
+        else twoPhaseCollideKernel<L, false, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
     } else {
-        if (mom) twoPhaseCollideKernel<L, true, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a);
-        else twoPhaseCollideKernel<L, false, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a);
+        if (mom) twoPhaseCollideKernel<L, true, IDX_TABLE><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
+        else twoPhaseCollideKernel<L, false, IDX_TABLE><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
     }
     ++g_launches;
 }

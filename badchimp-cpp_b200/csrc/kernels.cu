@@ -57,9 +57,18 @@ __global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks,
                                 double *sumOut, double *forceX, int finish)
 {
     __shared__ double sh[8];
-    double v = 0.0;
-    for (int b = threadIdx.x; b < nBlocks; b += blockDim.x) v += partial[b];
-    const double s = blockSum256(v, sh);
+    // four independent accumulators per thread keep several loads in flight; the summation order is
+    // fixed by (thread, slot), so the result is deterministic
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    int b = threadIdx.x;
+    for (; b + 3 * (int)blockDim.x < nBlocks; b += 4 * blockDim.x) {
+        v0 += partial[b];
+        v1 += partial[b + blockDim.x];
+        v2 += partial[b + 2 * blockDim.x];
+        v3 += partial[b + 3 * blockDim.x];
+    }
+    for (; b < nBlocks; b += blockDim.x) v0 += partial[b];
+    const double s = blockSum256((v0 + v1) + (v2 + v3), sh);
     if (threadIdx.x == 0) {
         *sumOut = s;
         if (finish) {

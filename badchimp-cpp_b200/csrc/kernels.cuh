@@ -34,6 +34,17 @@ namespace chimp {
 #define CHIMP_MIN_BLOCKS 6
 #endif
 
+// two-phase kernels: collide (pass D) and moments (passes A + C; its block reduction assumes 256 threads)
+#ifndef CHIMP_TP_BLOCK
+#define CHIMP_TP_BLOCK 128
+#endif
+#ifndef CHIMP_TP_MIN_BLOCKS
+#define CHIMP_TP_MIN_BLOCKS 4
+#endif
+#ifndef CHIMP_PM_MIN_BLOCKS
+#define CHIMP_PM_MIN_BLOCKS 3
+#endif
+
 enum { COLL_BGK = 0, COLL_TRT = 1 };
 enum { IDX_TABLE = 0, IDX_COMPACT = 1 };
 
@@ -344,7 +355,7 @@ struct TwoPhaseArgs {
 };
 
 template <class L, int IDX>
-__global__ void __launch_bounds__(256) phaseMomentsKernel(const TwoPhaseArgs a)
+__global__ void __launch_bounds__(256, CHIMP_PM_MIN_BLOCKS) phaseMomentsKernel(const TwoPhaseArgs a)
 {
     __shared__ double sh[8];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,12 +384,28 @@ __global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks,
                                 double *sumOut, double *forceX, int finish);
 
 template <class L, bool MOM, int IDX>
-__global__ void __launch_bounds__(256) twoPhaseCollideKernel(const TwoPhaseArgs a)
+__global__ void __launch_bounds__(CHIMP_TP_BLOCK, CHIMP_TP_MIN_BLOCKS) twoPhaseCollideKernel(const TwoPhaseArgs a)
 {
     const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.end;
     if (IDX == IDX_TABLE && !live) return;
     if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return;
+    // colour gradient first (LButilities.h:12-22 -> LBd3q19.h:155-163): its Q gathered scalars are reduced
+    // to nD numbers before the populations occupy the registers
+    double g[3] = {0.0, 0.0, 0.0};
+    double CGNorm = 0.0;
+    if (live) {
+        double ph[L::nQ];
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) ph[q] = a.phi[__ldg(a.ptable + ((unsigned)q * (unsigned)a.nPad + (unsigned)i))];
+        g[0] = latticeGrad<L, 0>(ph);
+        g[1] = latticeGrad<L, 1>(ph);
+        if (L::nD == 3) g[2] = latticeGrad<L, 2>(ph);
+        CGNorm = sqrt(dotD<L>(g, g));
+        const double inv = 1.0 / (CGNorm + (CGNorm < 2.220446049250313e-16 ? 1.0 : 0.0)); // lbBaseEps (LBglobal.h:14)
+#pragma unroll
+        for (int d = 0; d < L::nD; ++d) g[d] *= inv;
+    }
     double fTot[L::nQ];
     const long long field1 = (long long)L::nQ * a.stride;
     forEachSource<L, IDX>(a, i, live, [&](int q, const double *p) {
@@ -401,41 +428,44 @@ __global__ void __launch_bounds__(256) twoPhaseCollideKernel(const TwoPhaseArgs 
     const double tauInv = 1.0 / tau, tauFactor = (1 - 0.5 / tau);
     const double uu = dotD<L>(u, u);
     const double uF = dotD<L>(u, F);
-    // colour gradient (LButilities.h:12-22 -> LBd3q19.h:155-163)
-    double ph[L::nQ];
-#pragma unroll
-    for (int q = 0; q < L::nQ; ++q) ph[q] = a.phi[__ldg(a.ptable + (long long)q * a.nPad + i)];
-    double g[3] = {0.0, 0.0, 0.0};
-    g[0] = latticeGrad<L, 0>(ph);
-    g[1] = latticeGrad<L, 1>(ph);
-    if (L::nD == 3) g[2] = latticeGrad<L, 2>(ph);
-    const double CGNorm = sqrt(dotD<L>(g, g));
-    const double inv = 1.0 / (CGNorm + (CGNorm < 2.220446049250313e-16 ? 1.0 : 0.0)); // lbBaseEps (LBglobal.h:14)
-#pragma unroll
-    for (int d = 0; d < L::nD; ++d) g[d] *= inv;
     const double AF0_5 = 1.125 * CGNorm * a.sigma / tau;      // LBcollision2phase.h:12
     const double rhoFacBeta = a.beta * rho0 * rho1 / rho;     // LBcollision2phase.h:74
     const double c0 = (rho0 / rho), c1 = (rho1 / rho);
-    auto body = [&](auto qc) {
-        constexpr int q = decltype(qc)::value;
+    // opposite directions share every even intermediate and negate every odd one exactly (see the
+    // single-field kernel); this also halves the divisions by |c_q| in the recolouring term
+    const double c2uu = kC2 * uu, c2uF = kC2 * uF;
+    const double negTauInv = -tauInv;
+    auto pairBody = [&](auto pc) {
+        constexpr int q = decltype(pc)::value, r = q + L::nPairs;
         const double cu = cDot<L, q>(u);
         const double cF = cDot<L, q>(F);
-        const double om = omegaBGK<L, q>(fTot[q], tauInv, rho, cu, uu);
-        const double dF = deltaOmegaF<L, q>(tauFactor, cu, uF, cF);
-        double st, rc;
-        if (q < L::nQ - 1) {
-            const double cCG = cDot<L, q>(g);
-            st = AF0_5 * (L::w(q) * cCG * cCG - L::B(q));
-            rc = rhoFacBeta * L::w(q) * cCG / cNorm<L, q>();
-        } else {
-            st = -AF0_5 * L::B(q);
-            rc = 0.0;
-        }
-        const double common = fTot[q] + om + dF + st;
-        a.pl.out[q][i] = c0 * common + rc;
-        a.pl.out[q][field1 + i] = c1 * common - rc;
+        const double cCG = cDot<L, q>(g);
+        const double t = kC4Inv0_5 * (cu * cu - c2uu);
+        const double m3 = kC2Inv * cu;
+        const double rw = rho * L::w(q);
+        const double eq = 1.0 + m3 + t, er = 1.0 - m3 + t;
+        const double wtf = L::w(q) * tauFactor;
+        const double gF = kC4Inv * (cF * cu - c2uF);
+        const double h = kC2Inv * cF;
+        const double st = AF0_5 * (L::w(q) * cCG * cCG - L::B(q));     // LBcollision2phase.h:16
+        const double rc = rhoFacBeta * L::w(q) * cCG / cNorm<L, q>();  // LBcollision2phase.h:79
+        const double commonQ = fTot[q] + negTauInv * (fTot[q] - rw * eq) + wtf * (h + gF) + st;
+        const double commonR = fTot[r] + negTauInv * (fTot[r] - rw * er) + wtf * (gF - h) + st;
+        a.pl.out[q][i] = c0 * commonQ + rc;
+        a.pl.out[q][field1 + i] = c1 * commonQ - rc;
+        a.pl.out[r][i] = c0 * commonR - rc;
+        a.pl.out[r][field1 + i] = c1 * commonR + rc;
     };
-    staticFor<L::nQ>(body);
+    staticFor<L::nPairs>(pairBody);
+    {
+        constexpr int q = L::nQ - 1; // rest direction (LBcollision2phase.h:18,84)
+        const double om = omegaBGK<L, q>(fTot[q], tauInv, rho, 0.0, uu);
+        const double dF = deltaOmegaF<L, q>(tauFactor, 0.0, uF, 0.0);
+        const double st = -AF0_5 * L::B(q);
+        const double common = fTot[q] + om + dF + st;
+        a.pl.out[q][i] = c0 * common + 0.0;
+        a.pl.out[q][field1 + i] = c1 * common - 0.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -7,7 +7,32 @@
 #ifndef CHIMP_LBFIELD_H
 #define CHIMP_LBFIELD_H
 
+#include <fstream>
+
 #include "LBglobal.h"
+
+namespace chimp_host {
+// raw restart files of the reference (LBfield.h:102-138, 233-276, 378-421): int32 header + AoS doubles
+inline void writeRaw(const std::string &file, std::initializer_list<int> header, const lbBase_t *data, std::size_t n)
+{
+    std::ofstream ofs(file, std::ios::out | std::ios::binary);
+    if (!ofs) { std::cout << "Could not open file: " + file << std::endl; return; }
+    for (int h : header) ofs.write((const char *)&h, sizeof(int));
+    ofs.write((const char *)data, std::streamsize(n * sizeof(lbBase_t)));
+}
+inline bool readRaw(const std::string &file, std::initializer_list<int> expect, lbBase_t *data, std::size_t n)
+{
+    std::ifstream ifs(file, std::ios::in | std::ios::binary);
+    if (!ifs) { std::cout << "Could not open file: " + file << std::endl; return false; }
+    for (int e : expect) {
+        int h = 0;
+        ifs.read((char *)&h, sizeof(int));
+        if (h != e) { std::cout << "WARNNING: Mismatch between field size and read field size in file: " << file << "\n          No data read!" << std::endl; return false; }
+    }
+    ifs.read((char *)data, std::streamsize(n * sizeof(lbBase_t)));
+    return bool(ifs);
+}
+} // namespace chimp_host
 
 class ScalarField
 {
@@ -19,6 +44,8 @@ public:
     int getNumNodes() const { return nNodes_; }
     int size() const { return nNodes_; }
     lbBase_t *data() { return &data_[0]; }
+    void writeToFile(const std::string &fileName) const { chimp_host::writeRaw(fileName + ".lbsca", {nFields_, nNodes_}, &data_[0], data_.size()); }
+    void readFromFile(const std::string &fileName) { chimp_host::readRaw(fileName + ".lbsca", {nFields_, nNodes_}, &data_[0], data_.size()); }
 
 private:
     int nFields_, nNodes_;
@@ -49,6 +76,8 @@ public:
     int num_fields() const { return nFields_; }
     int getNumNodes() const { return nNodes_; }
     lbBase_t *data() { return &data_[0]; }
+    void writeToFile(const std::string &fileName) const { chimp_host::writeRaw(fileName + ".lbvec", {nFields_, DXQY::nD, nNodes_}, &data_[0], data_.size()); }
+    void readFromFile(const std::string &fileName) { chimp_host::readRaw(fileName + ".lbvec", {nFields_, DXQY::nD, nNodes_}, &data_[0], data_.size()); }
 
 private:
     int nFields_, nNodes_;
@@ -75,6 +104,8 @@ public:
     int getNumNodes() const { return nNodes_; }
     lbBase_t *data() { return &data_[0]; }
     const lbBase_t *data() const { return &data_[0]; }
+    void writeToFile(const std::string &fileName) const { chimp_host::writeRaw(fileName + ".lblbf", {nFields_, DXQY::nQ, nNodes_}, &data_[0], data_.size()); }
+    void readFromFile(const std::string &fileName) { chimp_host::readRaw(fileName + ".lblbf", {nFields_, DXQY::nQ, nNodes_}, &data_[0], data_.size()); }
 
 private:
     int nFields_, nNodes_;

@@ -35,7 +35,7 @@ DRIVER = os.path.join(HERE, "_ref", "ref_driver")
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attributes, keep_vtklb=False):
+def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attributes, keep_vtklb=False, checkpoint=False):
     d = tempfile.mkdtemp(prefix="golden_")
     os.makedirs(os.path.join(d, "out"))
     basis = lattice if lattice != "D3Q27" else G.BASIS["D3Q27"].astype(int)
@@ -46,6 +46,8 @@ def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attribu
     nranks = int(np.max(geo))
     cmd = [DRIVER, "--case", case, "--lattice", lattice, "--dir", d, "--out", os.path.join(d, "out"), "--nranks",
            str(nranks), "--steps", str(steps), "--dump", ",".join(str(s) for s in dump)] + [str(a) for a in args]
+    if checkpoint:
+        cmd += ["--checkpoint", os.path.join(OUT, name + ".ckpt")]
     subprocess.run(cmd, check=True, capture_output=True)
     gold = {"geo": np.asarray(geo, dtype=np.int32), "lattice": lattice, "periodic": periodic, "case": case,
             "steps": steps, "dump": np.array(dump), "args": np.array([str(a) for a in args]), "nranks": nranks}
@@ -127,7 +129,7 @@ def main():
     chan = np.ones((8, 12), dtype=int)
     chan[:, 0] = chan[:, -1] = 0
     run_reference("std_d2q9_channel", chan, "D2Q9", "x", "std_case", 20, [1, 2, 20], ["--tau", 0.8, "--force", "1e-6,0,0"],
-                  {"init_rho": np.ones(chan.shape)})
+                  {"init_rho": np.ones(chan.shape)}, checkpoint=True)
     pack2 = G.sphere_pack((16, 12), 2.5, 0.7, 5).astype(int)
     run_reference("std_d2q9_pack_p2", G.z_slab_rank_map(pack2, 2), "D2Q9", "xy", "std_case", 8, [1, 8],
                   ["--tau", 0.7, "--force", "1e-6,-2e-6,0"], {"init_rho": np.ones(pack2.shape)})

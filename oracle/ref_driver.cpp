@@ -62,6 +62,7 @@ struct Opts {
     int nranks = 1, steps = 1;
     std::set<int> dumpSteps;
     bool dumpTables = true, dumpF = true, timing = false;
+    std::string checkpoint; // prefix for the reference's own writeToFile() dumps after the last step
     double tau = 0.8, tauSym = 0.0, tauAnti = 0.0; // TRT when tauSym > 0
     std::vector<double> force{0, 0, 0};
     double tau0 = 1, tau1 = 1, sigma = 0.01, beta = 1, momx = 1e-5; // twophase
@@ -247,7 +248,14 @@ double runStdCase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid,
         bb.apply(f, grid);
         dump(i);
     }
-    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!o.checkpoint.empty()) { // LBfield.h:102-114, 233-247, 378-392
+        const std::string p = o.checkpoint + std::to_string(vtklb.getRank());
+        f.writeToFile(p);
+        rho.writeToFile(p);
+        vel.writeToFile(p);
+    }
+    return secs;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -585,6 +593,7 @@ int main(int argc, char **argv)
         else if (a == "--no-tables") o.dumpTables = false;
         else if (a == "--no-f") o.dumpF = false;
         else if (a == "--time") o.timing = true;
+        else if (a == "--checkpoint") o.checkpoint = next();
         else if (a == "--tau") o.tau = std::stod(next());
         else if (a == "--trt") { auto v = parseList(next()); o.tauSym = v[0]; o.tauAnti = v[1]; }
         else if (a == "--force") { auto v = parseList(next()); v.resize(3, 0.0); o.force = v; }
