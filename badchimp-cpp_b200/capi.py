@@ -54,7 +54,7 @@ SYMBOLS = [
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
-    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
+    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
 ]
 
 
@@ -275,11 +275,40 @@ class Lattice:
     def add_halo_face(self, rank, send_src, recv_dst):
         send_src = np.ascontiguousarray(send_src, dtype=np.int64)
         recv_dst = np.ascontiguousarray(recv_dst, dtype=np.int64)
+        if not hasattr(self, "_faces") or self._faces is None:
+            self._faces = []
+        self._faces.append((send_src, recv_dst))
         _check(lib().chimp_add_halo_face(self.h, C.c_int(rank), C.c_longlong(len(send_src)), _p(send_src),
                                          C.c_longlong(len(recv_dst)), _p(recv_dst)))
 
     def set_boundary_count(self, n):
         _check(lib().chimp_set_boundary_count(self.h, C.c_int(n)))
+
+    def ipc_handles(self):
+        buf = (C.c_ubyte * 192)()
+        _check(lib().chimp_ipc_handles(self.h, buf))
+        return bytes(buf)
+
+    def local_pointers(self):
+        out = (C.c_void_p * 3)()
+        _check(lib().chimp_local_pointers(self.h, out))
+        return [int(x) if x else 0 for x in out]
+
+    def recv_dst(self, k):
+        """slot offsets (q*plane_stride + slot) of my receive list for neighbour / face k"""
+        faces = getattr(self, "_faces", None)
+        return faces[k][1] if faces else self.host_halo_lists(k)[2]
+
+    def connect_peer(self, k, peer_field_stride, peer_face, peer_dst, handles=None, pointers=None):
+        peer_dst = np.ascontiguousarray(peer_dst, dtype=np.int64)
+        hb = (C.c_ubyte * 192).from_buffer_copy(handles) if handles is not None else None
+        pp = (C.c_void_p * 3)(*pointers) if pointers is not None else None
+        _check(lib().chimp_connect_peer(self.h, C.c_int(k), hb, C.c_int(1 if pointers is not None else 0), pp,
+                                        C.c_longlong(peer_field_stride), C.c_int(peer_face), C.c_longlong(len(peer_dst)),
+                                        _p(peer_dst)))
+
+    def plane_stride(self):
+        return int(lib().chimp_plane_stride(self.h))
 
     def halo_stream(self):
         return lib().chimp_halo_stream(self.h)

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <climits>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,9 @@ namespace chimp {
 __global__ void fluxForceKernel(const double *, int, double, double, double *, double *, int);
 __global__ void massFinalizeKernel(const double *, int, const double *, double *, double *);
 __global__ void fillKernel(double *p, double v, long long count);
+__global__ void haloPushKernel(double *, const double *, const long long *, const long long *, int, int, long long, long long,
+                               unsigned *, unsigned long long *, unsigned long long);
+__global__ void waitFlagKernel(const unsigned long long *, unsigned long long);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *, int, long long);
 __global__ void kernelTableKernel(const int32_t *, int32_t *, int, int, int, int, long long);
@@ -37,6 +41,7 @@ using namespace chimp;
 namespace {
 
 thread_local std::string g_err;
+std::map<std::string, void *> g_ipcOpen; // CUDA IPC mappings of this process (kept until exit)
 std::atomic<long long> g_launches{0};
 
 int fail(const char *fmt, ...)
@@ -78,6 +83,13 @@ struct Neighbor {
     long long *d_phiSendSrc = nullptr, *d_phiRecvDst = nullptr; // scalar (phi) halo: slots of the phi array
     double *d_phiSendBuf = nullptr, *d_phiRecvBuf = nullptr;
     long long phiSendCount = 0, phiRecvCount = 0;
+    // peer halos (CUDA IPC): the neighbour's two population buffers and its arrival flag for my face
+    double *peerX[2] = {nullptr, nullptr};
+    unsigned long long *peerFlags = nullptr;
+    long long *d_peerDst = nullptr;
+    long long peerFieldStride = 0;
+    int peerFace = -1;
+    unsigned *d_blockCounter = nullptr;
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;   // owned
     double *x_sendBuf = nullptr, *x_recvBuf = nullptr;   // caller-owned overrides (chimp_set_halo_buffers)
     double *sendBuf() const { return x_sendBuf ? x_sendBuf : d_sendBuf; }
@@ -144,6 +156,8 @@ struct chimp_lattice {
     cudaEvent_t evBoundary = nullptr, evHalo = nullptr, evStep = nullptr;
     chimp_exchange_fn exchange = nullptr, scalarExchange = nullptr;
     void *exchangeUser = nullptr, *scalarExchangeUser = nullptr;
+    unsigned long long *d_flags = nullptr; // arrival counters written by the neighbours, one per face (max 8)
+    bool peerHalos = false;
     chimp_allreduce_fn allreduce = nullptr;
     void *allreduceUser = nullptr;
     std::vector<std::vector<long long>> hPhiSendSrc, hPhiRecvDst;
@@ -171,6 +185,8 @@ int allocateState(chimp_lattice *c)
     CUDA_OK(cudaMalloc(&c->d_vel, (size_t)c->nPad * c->li.nD * sizeof(double)));
     CUDA_OK(cudaMemsetAsync(c->d_rho, 0, (size_t)c->nPad * c->nFields * sizeof(double), c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_vel, 0, (size_t)c->nPad * c->li.nD * sizeof(double), c->stream));
+    CUDA_OK(cudaMalloc(&c->d_flags, 8 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(unsigned long long), c->stream));
     return 0;
 }
 
@@ -772,11 +788,12 @@ void chimp_destroy(chimp_lattice *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     freeDev(c->d_table); freeDev(c->d_ktable); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
-    freeDev(c->d_rho); freeDev(c->d_vel);
+    freeDev(c->d_rho); freeDev(c->d_vel); freeDev(c->d_flags);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
     for (auto &nb : c->nbrs) {
+        freeDev(nb.d_peerDst); freeDev(nb.d_blockCounter);
         freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf);
         freeDev(nb.d_phiSendSrc); freeDev(nb.d_phiRecvDst); freeDev(nb.d_phiSendBuf); freeDev(nb.d_phiRecvBuf);
     }
@@ -1038,9 +1055,34 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom, bool cal
     // new one.  evStep orders the halo stream behind everything the main stream did up to here.
     CUDA_OK(cudaEventRecord(c->evStep, c->stream));
     CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evStep, 0));
+    if (c->peerHalos) {
+        // the halo-in slots of the buffer read now were stored by the neighbours during their previous
+        // step: wait until every face has reported that step (the flag counts completed pushes)
+        for (size_t k = 0; k < c->nbrs.size(); ++k) {
+            waitFlagKernel<<<1, 1, 0, c->haloStream>>>(c->d_flags + k, (unsigned long long)c->steps);
+            ++g_launches;
+        }
+    }
     a.begin = 0;
     a.end = c->nBoundary ? c->nBoundary : c->n;
     dispatchSingleLattice(c, a, p->collision, mom, c->haloStream);
+    if (c->peerHalos) {
+        const long long fieldStride = (long long)c->li.nQ * c->stride;
+        const int outIdx = c->cur ^ 1;
+        for (auto &nb : c->nbrs)
+            if (nb.sendCount) {
+                haloPushKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->haloStream>>>(
+                    nb.peerX[outIdx], foutBuf, nb.d_sendSrc, nb.d_peerDst, (int)nb.sendCount, c->nFields, fieldStride,
+                    nb.peerFieldStride, nb.d_blockCounter, nb.peerFlags + nb.peerFace, (unsigned long long)(c->steps + 1));
+                ++g_launches;
+            }
+        if (c->nBoundary && c->nBoundary < c->n) {
+            a.begin = c->nBoundary;
+            a.end = c->n;
+            dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+        }
+        return 0;
+    }
     packHalos(c, foutBuf);
     // the transport is enqueued before the interior launch so that it is ahead of it in issue order
     if (callExchange && c->exchange && c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
@@ -1057,7 +1099,7 @@ int stepEnd(chimp_lattice *c)
 {
     double *fout = c->d_f[c->cur ^ 1];
     if (!c->nbrs.empty()) {
-        unpackHalos(c, fout);
+        if (!c->peerHalos) unpackHalos(c, fout);
         CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
     }
@@ -1407,6 +1449,79 @@ int chimp_add_halo_face(chimp_lattice *c, int neig_rank, long long n_send, const
         CUDA_OK(cudaMalloc(&nb.d_recvBuf, (size_t)n_recv * c->nFields * sizeof(double)));
     }
     c->nbrs.push_back(std::move(nb));
+    return 0;
+}
+
+int chimp_ipc_handles(chimp_lattice *c, unsigned char *out192)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    void *ptrs[3] = {c->d_f[0], c->d_f[1], c->d_flags};
+    for (int k = 0; k < 3; ++k) {
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaIpcGetMemHandle(&h, ptrs[k]));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(out192 + 64 * k, &h, 64);
+    }
+    return 0;
+}
+
+int chimp_connect_peer(chimp_lattice *c, int k, const unsigned char *peer_handles192, int same_process,
+                       void *const *peer_ptrs3, long long peer_field_stride, int peer_face, long long n_dst,
+                       const long long *peer_dst)
+{
+    if (check(c, true)) return 1;
+    if (k < 0 || k >= (int)c->nbrs.size() || k >= 8) return fail("bad neighbour index");
+    if (peer_face < 0 || peer_face >= 8) return fail("bad peer face index");
+    Neighbor &nb = c->nbrs[k];
+    if (n_dst != nb.sendCount) return fail("peer destination list has %lld entries, my send list %lld", n_dst, nb.sendCount);
+    CUDA_OK(cudaSetDevice(c->device));
+    void *ptrs[3] = {nullptr, nullptr, nullptr};
+    if (same_process) {
+        // both contexts live in this process (tests): the peer's device pointers are directly usable
+        for (int j = 0; j < 3; ++j) ptrs[j] = peer_ptrs3[j];
+    } else {
+        for (int j = 0; j < 3; ++j) {
+            // one mapping per handle and process (a 2-rank ring reaches the same peer through both faces)
+            const std::string key((const char *)peer_handles192 + 64 * j, 64);
+            auto it = g_ipcOpen.find(key);
+            if (it == g_ipcOpen.end()) {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, peer_handles192 + 64 * j, 64);
+                void *p = nullptr;
+                CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                it = g_ipcOpen.emplace(key, p).first;
+            }
+            ptrs[j] = it->second;
+        }
+    }
+    nb.peerX[0] = (double *)ptrs[0];
+    nb.peerX[1] = (double *)ptrs[1];
+    nb.peerFlags = (unsigned long long *)ptrs[2];
+    nb.peerFieldStride = peer_field_stride;
+    nb.peerFace = peer_face;
+    freeDev(nb.d_peerDst);
+    if (n_dst) {
+        CUDA_OK(cudaMalloc(&nb.d_peerDst, (size_t)n_dst * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(nb.d_peerDst, peer_dst, (size_t)n_dst * sizeof(long long), cudaMemcpyHostToDevice));
+    }
+    if (!nb.d_blockCounter) {
+        CUDA_OK(cudaMalloc(&nb.d_blockCounter, sizeof(unsigned)));
+        CUDA_OK(cudaMemset(nb.d_blockCounter, 0, sizeof(unsigned)));
+    }
+    bool all = true;
+    for (auto &x : c->nbrs) all = all && x.peerFlags != nullptr;
+    c->peerHalos = all;
+    return 0;
+}
+
+int chimp_local_pointers(chimp_lattice *c, void **out3)
+{
+    if (check(c, true)) return 1;
+    out3[0] = c->d_f[0];
+    out3[1] = c->d_f[1];
+    out3[2] = c->d_flags;
     return 0;
 }
 

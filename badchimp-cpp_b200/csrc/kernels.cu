@@ -26,6 +26,37 @@ __global__ void haloUnpackKernel(double *X, const double *__restrict__ buf, cons
     if (k < count) X[dst[k]] = buf[k];
 }
 
+__global__ void haloPushKernel(double *peerX, const double *__restrict__ X, const long long *__restrict__ src,
+                               const long long *__restrict__ dst, int count, int nFields, long long fieldStride,
+                               long long peerFieldStride, unsigned *blockCounter, unsigned long long *peerFlag,
+                               unsigned long long value)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) {
+        const long long s = src[k], d = dst[k];
+        for (int f = 0; f < nFields; ++f) peerX[d + f * peerFieldStride] = X[s + f * fieldStride];
+    }
+    // every thread's remote stores are ordered before the flag: fence, count blocks, last one signals
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(blockCounter, 1u);
+        if (done == gridDim.x - 1) {
+            *blockCounter = 0u;
+            __threadfence_system();
+            *(volatile unsigned long long *)peerFlag = value;
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect)
+{
+    const volatile unsigned long long *f = flag;
+    while (*f < expect) __nanosleep(200);
+    __threadfence_system();
+}
+
 __global__ void fillKernel(double *p, double v, long long count)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -536,6 +536,15 @@ __global__ void gatherStateKernel(double *aos, const double *__restrict__ X, con
 __global__ void planesToAosKernel(double *aos, const double *__restrict__ planes, const int32_t *__restrict__ label,
                                   int n, int nPad, int nComp, int aosStride, int aosOffset);
 
+// Peer halos: the outgoing populations are stored straight into the neighbour GPU's halo-in slots over
+// NVLink (peerX is the peer's buffer, mapped through CUDA IPC), field by field; the last block to finish
+// publishes the step number in the peer's arrival flag.  waitFlagKernel is the consumer side.
+__global__ void haloPushKernel(double *peerX, const double *__restrict__ X, const long long *__restrict__ src,
+                               const long long *__restrict__ dst, int count, int nFields, long long fieldStride,
+                               long long peerFieldStride, unsigned *blockCounter, unsigned long long *peerFlag,
+                               unsigned long long value);
+__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect);
+
 // halo pack: buf[k] = X[src[k]] ; unpack: X[dst[k]] = buf[k]   (64-bit slot offsets)
 __global__ void haloPackKernel(double *__restrict__ buf, const double *__restrict__ X,
                                const long long *__restrict__ src, int count);

@@ -67,6 +67,25 @@ def attach_ring(lat, slab, rank, world, device):
     return ring
 
 
+def attach_ring_peer(lat, slab, rank, world):
+    """registers the two halo faces and connects them to the neighbour GPUs' memory (CUDA IPC): the engine
+    then stores outgoing populations straight into the peers' halo-in slots, no NCCL and no host callback
+    per step.  torch.distributed only carries the one-time handshake (IPC handles + receive lists)."""
+    faces = slab["faces"]
+    down, up = (rank - 1) % world, (rank + 1) % world
+    lat.add_halo_face(down, faces["down"][0].cpu().numpy(), faces["down"][1].cpu().numpy())
+    lat.add_halo_face(up, faces["up"][0].cpu().numpy(), faces["up"][1].cpu().numpy())
+    lat.set_boundary_count(slab["n_boundary"])
+    info = {"handles": lat.ipc_handles(), "field_stride": lat.nq * lat.plane_stride(),
+            "recv_down": faces["down"][1].cpu().numpy(), "recv_up": faces["up"][1].cpu().numpy()}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, info)
+    # what I send down lands in the "up" face (index 1) of rank-1, what I send up in the "down" face (0) of rank+1
+    lat.connect_peer(0, everyone[down]["field_stride"], 1, everyone[down]["recv_up"], handles=everyone[down]["handles"])
+    lat.connect_peer(1, everyone[up]["field_stride"], 0, everyone[up]["recv_down"], handles=everyone[up]["handles"])
+    dist.barrier()
+
+
 def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
     """bench.py --gpus N (N > 1): every rank owns one size^3 block of a size x size x (size N) pack"""
     from . import bench_impl as B
@@ -98,7 +117,13 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
     index_form = capi.INDEX_COMPACT if args.index == "compact" else capi.INDEX_TABLE
     lat = capi.lattice_from_device_table(lattice, slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
                                          slab["labels"].data_ptr(), 1, index_form, local)
-    attach_ring(lat, slab, rank, world, device)
+    halo_mode = getattr(args, "halo", "peer")
+    if halo_mode == "peer":
+        attach_ring_peer(lat, slab, rank, world)
+        halo_bytes = 8.0 * (len(slab["faces"]["down"][0]) + len(slab["faces"]["up"][0]))
+    else:
+        attach_ring(lat, slab, rank, world, device)
+        halo_bytes = 8.0 * (sum(lat._ring.counts[0::2]))
     n = slab["n"]
     slab["table"] = slab["labels"] = None
     torch.cuda.empty_cache()
@@ -174,9 +199,10 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "std_case physics (D3Q19 BGK + Guo force + half-way bounce back), periodic random sphere pack %dx%dx%d (one %d^3 block per GPU, z-slabs), R=%d, seed 1234" % (size, size, size * world, size, size // 8),
-                           "fluid_nodes": n_total, "index_form": args.index, "parallelism": "z-slab x%d, NCCL send/recv halos overlapped with interior nodes" % world,
+                           "fluid_nodes": n_total, "index_form": args.index, "parallelism": "z-slab x%d, halos overlapped with interior nodes" % world,
                            "l2_policy": "state per GPU 2 x %.1f GB >> 126 MB L2" % (n * 152 / 1e9),
-                           "halo_bytes_per_step_per_gpu": 8.0 * (sum(lat._ring.counts[0::2])),
+                           "halo_bytes_per_step_per_gpu": halo_bytes,
+                           "halo_transport": "peer stores over NVLink from the halo-coupled part of the step (CUDA IPC)" if halo_mode == "peer" else "NCCL send/recv (torch.distributed) between pack and unpack kernels",
                            "slabs": "balanced by fluid-node count" if getattr(args, "balance", True) else "equal thickness",
                            "nodes_per_rank": [int(x) for x in per_rank[:, 0]], "ms_per_step_per_rank": [round(float(x), 4) for x in per_rank[:, 1]],
                            "slab_thickness_per_rank": [int(x) for x in per_rank[:, 2]],

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="edge length of the cubic sphere pack (0 = default)")
     ap.add_argument("--index", default="compact", choices=["compact", "table"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N>1: halo transport")
     ap.add_argument("--no-balance", dest="balance", action="store_false", help="N>1: equal-thickness z-slabs instead of equal fluid-node counts")
     args = ap.parse_args()
     import helpers

@@ -168,6 +168,21 @@ void *chimp_halo_stream(chimp_lattice *);
  * their order defines the packed message.  The same rank may own two faces (2-rank ring). */
 int chimp_add_halo_face(chimp_lattice *, int neig_rank, long long n_send, const long long *send_src,
                         long long n_recv, const long long *recv_dst);
+/* Peer halos: instead of pack -> host transport -> unpack, the engine stores the outgoing populations
+ * directly into the neighbour GPU's halo-in slots over NVLink and publishes an arrival counter there
+ * (fused into the halo-coupled part of the step; replaces MPI_Send/MPI_Recv of LBmonlatmpi.h:253-257).
+ * chimp_ipc_handles: 3 x 64-byte CUDA IPC handles (population buffer A, buffer B, arrival flags) for the
+ * other process; chimp_connect_peer: what neighbour/face k of THIS lattice needs to know about its peer --
+ * the peer's handles (or, when both lattices live in one process, its raw pointers from
+ * chimp_local_pointers), the peer's field stride nQ*plane_stride, the index of the peer's face that I feed,
+ * and for each entry of my send list the slot offset q*peer_plane_stride + slot it lands in (the peer's
+ * receive list).  Once every neighbour is connected, stepping uses the peer path.  All ranks must step
+ * the same number of times. */
+int chimp_ipc_handles(chimp_lattice *, unsigned char *out192);
+int chimp_local_pointers(chimp_lattice *, void **out3);
+int chimp_connect_peer(chimp_lattice *, int k, const unsigned char *peer_handles192, int same_process,
+                       void *const *peer_ptrs3, long long peer_field_stride, int peer_face, long long n_dst,
+                       const long long *peer_dst);
 /* the first n_boundary slots hold the halo-coupled nodes: they are stepped and packed first */
 int chimp_set_boundary_count(chimp_lattice *, int n_boundary);
 typedef int (*chimp_exchange_fn)(void *user, void *stream);

@@ -41,7 +41,10 @@ def main():
         slab = ingest.build_slab_tables(torch.from_numpy(ext).to(dev).bool(), lattice, True)
         lat = capi.lattice_from_device_table(lattice, slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
                                              slab["labels"].data_ptr(), 1, capi.INDEX_COMPACT, local)
-        multi.attach_ring(lat, slab, rank, world, dev)
+        if os.environ.get("CHIMP_HALO", "peer") == "peer":
+            multi.attach_ring_peer(lat, slab, rank, world)
+        else:
+            multi.attach_ring(lat, slab, rank, world, dev)
         lat.init_uniform(1.0)
         lat.step_single(steps, tau=0.8, force=(1e-5, 2e-6, -1e-6))
         rho, vel = lat.download_moments_device_order()
