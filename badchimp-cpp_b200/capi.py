@@ -54,7 +54,7 @@ SYMBOLS = [
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
-    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
+    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_node_list_flux", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
 ]
 
 
@@ -267,6 +267,22 @@ class Lattice:
     def download_mass_change(self, n_labels):
         out = np.zeros(n_labels)
         _check(lib().chimp_download_mass_change(self.h, _p(out)))
+        return out
+
+    def flux_force(self, field_no, cart_dir, fixed_flux, n_nodes_global):
+        """calcFluxForceCartDir (LBglobalforcing.h:8-33)"""
+        out = C.c_double(0.0)
+        _check(lib().chimp_flux_force(self.h, C.c_int(field_no), C.c_int(cart_dir), C.c_double(fixed_flux),
+                                      C.c_longlong(n_nodes_global), C.byref(out)))
+        return out.value
+
+    def node_list_flux(self, nodes, bins, n_bins, field_no=0, component=2):
+        """sum over the list of vel(component, n) * rho(field, n) per bin, in list order
+        (mass flux through the pressure nodes, std_one_phase/main.cpp:607-619)"""
+        nodes, bins = _i32(nodes), _i32(bins)
+        out = np.zeros(n_bins)
+        _check(lib().chimp_node_list_flux(self.h, C.c_int(len(nodes)), _p(nodes), _p(bins), C.c_int(n_bins), C.c_int(field_no),
+                                          C.c_int(component), _p(out)))
         return out
 
     def set_halo_buffers(self, k, send_ptr, recv_ptr):

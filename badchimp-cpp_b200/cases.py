@@ -83,6 +83,10 @@ def one_phase_setup(lg: G.LatticeGeometry, tabs, attrs):
         pr["press_links"] = links(4, 3)
         pr["fluid_links"] = links(2, 2, need_phase=1)
         pr["scale"] = scale
+        # findPressureFluidNodes (main.cpp:80-93) and the phase each contributes to (:610)
+        press = n[mine & (((tags >> 4) & 1) == 1)]
+        pr["press_nodes"] = press.astype(np.int32)
+        pr["press_phase"] = ((tags[press] & 3) - 1).astype(np.int32)
         # the initial state: rho = 1, u = 0, f = calcfeq(1, 0, 0) = w_q on bulk (main.cpp:441-474)
         f = np.zeros((t.size, 1, lg.nq))
         f[t.bulk_nodes(), 0, :] = lattice_weights(lg.lattice)[None, :]
@@ -116,3 +120,17 @@ def two_phase_setup(lg: G.LatticeGeometry, tabs, rho0, rho1, wettability):
             f[bulk, fld, :] = (w[None, :] * rho[bulk, fld, None]) * 1.0
         out.append(dict(rho=rho, f0=f, solid_bnd=t.solid_bnd_nodes()))
     return out
+
+
+def one_phase_mass_flux(lat, setup, old=(0.0, 0.0)):
+    """std_one_phase/main.cpp:607-633: mass flux of each phase through this rank's pressure-boundary
+    nodes, q_s = 0.5 * sum vel_z * rho, and its relative change since the previous write.  The products
+    are formed on the device from the moments of the last step; across ranks the caller adds the two
+    local sums (MPI_Allreduce at :619)."""
+    phase = setup["press_phase"]
+    if len(phase) and (phase.min() < 0 or phase.max() > 1):
+        raise ValueError("Fluid phase = %d in write mass flux" % int(phase[(phase < 0) | (phase > 1)][0]))
+    local = lat.node_list_flux(setup["press_nodes"], phase, 2, 0, 2)
+    q = 0.5 * local
+    change = (q - np.asarray(old)) / (q + 1e-15)
+    return local, q, change

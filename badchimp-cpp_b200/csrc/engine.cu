@@ -28,6 +28,8 @@ namespace chimp {
 __global__ void fluxForceKernel(const double *, int, double, double, double *, double *, int);
 __global__ void massFinalizeKernel(const double *, int, const double *, double *, double *);
 __global__ void fillKernel(double *p, double v, long long count);
+__global__ void invertLabelsKernel(const int32_t *, int, int32_t *);
+__global__ void nodeFluxKernel(const int32_t *, int, const int32_t *, int, const double *, const double *, double *);
 __global__ void haloPushKernel(double *, const double *, const long long *, const long long *, int, int, long long, long long,
                                unsigned *, unsigned long long *, unsigned long long);
 __global__ void waitFlagKernel(const unsigned long long *, unsigned long long);
@@ -161,6 +163,7 @@ struct chimp_lattice {
     chimp_allreduce_fn allreduce = nullptr;
     void *allreduceUser = nullptr;
     std::vector<std::vector<long long>> hPhiSendSrc, hPhiRecvDst;
+    int32_t *d_slotOf = nullptr; // reference label -> device slot (-1: not an own node), built on first use
     long long steps = 0;
 };
 
@@ -788,7 +791,7 @@ void chimp_destroy(chimp_lattice *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     freeDev(c->d_table); freeDev(c->d_ktable); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
-    freeDev(c->d_rho); freeDev(c->d_vel); freeDev(c->d_flags);
+    freeDev(c->d_rho); freeDev(c->d_vel); freeDev(c->d_flags); freeDev(c->d_slotOf);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
@@ -1403,6 +1406,97 @@ double chimp_last_flux_force(chimp_lattice *c)
 }
 
 // ---- halo plumbing ----------------------------------------------------------------------
+extern "C++" {
+namespace {
+template <class L>
+void launchMomentumSum(chimp_lattice *c, const StepArgs &a, long long fieldOff, int cartDir, unsigned grid)
+{
+    if (c->indexForm == CHIMP_INDEX_COMPACT) momentumSumKernel<L, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a, fieldOff, cartDir, c->d_fluxPartial);
+    else momentumSumKernel<L, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a, fieldOff, cartDir, c->d_fluxPartial);
+    ++g_launches;
+}
+} // namespace
+} // extern "C++"
+
+int chimp_flux_force(chimp_lattice *c, int field_no, int cart_dir, double fixed_flux, long long n_nodes_global, double *force_out)
+{
+    if (check(c, true)) return 1;
+    if (field_no < 0 || field_no >= c->nFields) return fail("field %d out of range", field_no);
+    if (cart_dir < 0 || cart_dir >= c->li.nD) return fail("cartesian direction %d out of range", cart_dir);
+    if (n_nodes_global <= 0 || !force_out) return fail("bad arguments");
+    if (!c->nbrs.empty() && !c->allreduce) return fail("flux force across ranks needs chimp_set_allreduce_callback (LBglobalforcing.h:28)");
+    CUDA_OK(cudaSetDevice(c->device));
+    const unsigned grid = (unsigned)((c->n + 255) / 256);
+    if (!c->d_fluxPartial) CUDA_OK(cudaMalloc(&c->d_fluxPartial, (size_t)std::max(grid, 1u) * sizeof(double)));
+    if (!c->d_fluxSum) CUDA_OK(cudaMalloc(&c->d_fluxSum, sizeof(double)));
+    if (!c->d_forceX) CUDA_OK(cudaMalloc(&c->d_forceX, sizeof(double)));
+    StepArgs a{};
+    a.stride = c->stride;
+    a.n = c->n;
+    a.nPad = c->nPad;
+    fillIndexView(c, a.idx);
+    fillPlanes(c, a.pl);
+    const long long fieldOff = (long long)field_no * c->li.nQ * c->stride;
+    switch (c->lattice) {
+    case CHIMP_D2Q9: launchMomentumSum<D2Q9>(c, a, fieldOff, cart_dir, grid); break;
+    case CHIMP_D3Q19: launchMomentumSum<D3Q19>(c, a, fieldOff, cart_dir, grid); break;
+    case CHIMP_D3Q27: launchMomentumSum<D3Q27>(c, a, fieldOff, cart_dir, grid); break;
+    }
+    const bool multi = !c->nbrs.empty();
+    fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)grid, fixed_flux, (double)n_nodes_global, c->d_fluxSum, c->d_forceX, multi ? 0 : 1);
+    ++g_launches;
+    if (multi) {
+        if (c->allreduce(c->allreduceUser, c->d_fluxSum, 1, (void *)c->stream)) return fail("allreduce callback failed");
+        fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxSum, 1, fixed_flux, (double)n_nodes_global, c->d_fluxSum, c->d_forceX, 1);
+        ++g_launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(force_out, c->d_forceX, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int chimp_node_list_flux(chimp_lattice *c, int n_list, const int32_t *nodes, const int32_t *bin, int n_bins, int field_no,
+                         int component, double *out)
+{
+    if (check(c, true)) return 1;
+    if (n_list < 0 || (n_list && (!nodes || !bin)) || n_bins <= 0 || !out) return fail("bad arguments");
+    if (field_no < 0 || field_no >= c->nFields) return fail("field %d out of range", field_no);
+    if (component < 0 || component >= c->li.nD) return fail("velocity component %d out of range", component);
+    for (int k = 0; k < n_list; ++k)
+        if (bin[k] < 0 || bin[k] >= n_bins) return fail("bin %d of list entry %d out of range", bin[k], k);
+    CUDA_OK(cudaSetDevice(c->device));
+    for (int b = 0; b < n_bins; ++b) out[b] = 0.0;
+    if (n_list == 0) return 0;
+    if (labelRange(c)) return 1;
+    const int nLabels = c->labelMax + 1;
+    if (!c->d_slotOf) {
+        CUDA_OK(cudaMalloc(&c->d_slotOf, (size_t)nLabels * sizeof(int32_t)));
+        CUDA_OK(cudaMemsetAsync(c->d_slotOf, 0xff, (size_t)nLabels * sizeof(int32_t), c->stream));
+        invertLabelsKernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_label, c->n, c->d_slotOf);
+        ++g_launches;
+    }
+    int32_t *d_nodes = nullptr;
+    double *d_out = nullptr;
+    CUDA_OK(cudaMalloc(&d_nodes, (size_t)n_list * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&d_out, (size_t)n_list * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(d_nodes, nodes, (size_t)n_list * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    nodeFluxKernel<<<(unsigned)((n_list + 255) / 256), 256, 0, c->stream>>>(d_nodes, n_list, c->d_slotOf, nLabels,
+                                                                           c->d_rho + (size_t)field_no * c->nPad,
+                                                                           c->d_vel + (size_t)component * c->nPad, d_out);
+    ++g_launches;
+    std::vector<double> prod(n_list);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prod.data(), d_out, (size_t)n_list * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_nodes);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail("node list flux failed: %s", cudaGetErrorString(e));
+    // the reference adds the products in list order (std_one_phase/main.cpp:609-618)
+    for (int k = 0; k < n_list; ++k) out[bin[k]] += prod[k];
+    return 0;
+}
+
 int chimp_num_neighbors(chimp_lattice *c) { return c ? (int)c->nbrs.size() : 0; }
 int chimp_neighbor_info(chimp_lattice *c, int k, int *neig_rank, long long *send_count, long long *recv_count)
 {

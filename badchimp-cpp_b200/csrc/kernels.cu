@@ -57,6 +57,23 @@ __global__ void waitFlagKernel(const unsigned long long *flag, unsigned long lon
     __threadfence_system();
 }
 
+__global__ void invertLabelsKernel(const int32_t *__restrict__ label, int n, int32_t *__restrict__ slotOf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slotOf[label[i]] = i;
+}
+
+__global__ void nodeFluxKernel(const int32_t *__restrict__ nodes, int count, const int32_t *__restrict__ slotOf, int nLabels,
+                               const double *__restrict__ rho, const double *__restrict__ velComp, double *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int node = nodes[k];
+    const int s = (node >= 0 && node < nLabels) ? slotOf[node] : -1;
+    // rows of the reference fields that no own node writes stay zero-initialised (LBfield.h:75)
+    out[k] = s >= 0 ? velComp[s] * rho[s] : 0.0;
+}
+
 __global__ void fillKernel(double *p, double v, long long count)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;

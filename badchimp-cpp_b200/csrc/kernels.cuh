@@ -383,6 +383,28 @@ __global__ void __launch_bounds__(256, CHIMP_PM_MIN_BLOCKS) phaseMomentsKernel(c
 __global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks, double momx, double nGlobal,
                                 double *sumOut, double *forceX, int finish);
 
+// Library form of the flux controller (LBglobalforcing.h:8-33): per-block partial sums of
+// qSumC(f(fieldNo, n))[cartDir] over the own nodes; fluxForceKernel folds them.
+template <class L, int IDX>
+__global__ void __launch_bounds__(256) momentumSumKernel(const StepArgs a, long long fieldOff, int cartDir, double *partial)
+{
+    __shared__ double sh[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    double f[L::nQ];
+    Gather<L, IDX>::load(a, fieldOff, live ? i : 0, live, f);
+    double m = 0.0;
+    if (live) m = cartDir == 0 ? firstMoment<L, 0>(f) : (cartDir == 1 || L::nD == 2) ? firstMoment<L, 1>(f) : firstMoment<L, 2>(f);
+    const double s = blockSum256(m, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// Node-list products for callers (mass flux through the pressure nodes, std_one_phase/main.cpp:607-619):
+// out[k] = vel(component, node_k) * rho(field, node_k); the host adds them in list order like the reference.
+__global__ void invertLabelsKernel(const int32_t *__restrict__ label, int n, int32_t *__restrict__ slotOf);
+__global__ void nodeFluxKernel(const int32_t *__restrict__ nodes, int count, const int32_t *__restrict__ slotOf, int nLabels,
+                               const double *__restrict__ rho, const double *__restrict__ velComp, double *__restrict__ out);
+
 template <class L, bool MOM, int IDX>
 __global__ void __launch_bounds__(CHIMP_TP_BLOCK, CHIMP_TP_MIN_BLOCKS) twoPhaseCollideKernel(const TwoPhaseArgs a)
 {

@@ -9,5 +9,6 @@
 #include "LBhalfwaybb.h"
 #include "LBbndmpi.h"
 #include "LBgpu.h"
+#include "LBranks.h"
 #include "Input.h"
 #endif

@@ -74,6 +74,53 @@ public:
         for (int d = 0; d < DXQY::nD; ++d) p.force[d] = bodyForce[d];
         chimpCheck(chimp_step_single(h_, &p, nSteps));
     }
+    // std_one_phase: per-node attributes of main.cpp:253-345 (force switch, interior-domain label, mass-source
+    // marker, 1/count per interior domain) and the pressure-boundary density of :593; afterwards stepBGK /
+    // stepTRT run the loop of main.cpp:513-597
+    void setOnePhaseAttributes(ScalarField &forceOn, const std::vector<int> &interiorDomainsLabel, const std::vector<lbBase_t> &addMassSource,
+                               const std::vector<lbBase_t> &massSourceScaleFactor, lbBase_t rhoW)
+    {
+        chimpCheck(chimp_set_one_phase_attributes(h_, forceOn.data(), interiorDomainsLabel.data(), addMassSource.data(),
+                                                  int(massSourceScaleFactor.size()), massSourceScaleFactor.data(), rhoW));
+    }
+    std::vector<lbBase_t> massChange(int nLabels)
+    {
+        std::vector<lbBase_t> m(nLabels, 0.0);
+        chimpCheck(chimp_download_mass_change(h_, m.data()));
+        return m;
+    }
+    // massFluxLocal of main.cpp:606-618: sum of vel(0,2,n)*rho(0,n) over the pressure-boundary nodes, per fluid phase
+    std::vector<lbBase_t> massFlux(const std::vector<int> &pressureFluidNodes, const std::vector<int> &fluidPhase)
+    {
+        std::vector<lbBase_t> q(2, 0.0);
+        chimpCheck(chimp_node_list_flux(h_, int(pressureFluidNodes.size()), pressureFluidNodes.data(), fluidPhase.data(), 2, 0,
+                                        DXQY::nD - 1, q.data()));
+        return q;
+    }
+    // calcFluxForceCartDir (LBglobalforcing.h:8-33)
+    lbBase_t fluxForceCartDir(int fieldNo, int cartDir, lbBase_t fixedFlux, int numNodesGlobal)
+    {
+        lbBase_t F = 0.0;
+        chimpCheck(chimp_flux_force(h_, fieldNo, cartDir, fixedFlux, numNodesGlobal, &F));
+        return F;
+    }
+    // twophase: wall colour from rho(2,size) (main_TWOPHASE.cpp:173-181, 280-284), then nSteps iterations of :236-392
+    void setTwoPhaseDensity(ScalarField &rho) { chimpCheck(chimp_set_twophase_density(h_, rho.data())); }
+    void stepTwoPhase(lbBase_t tau0, lbBase_t tau1, lbBase_t sigma, lbBase_t beta, lbBase_t momx, const std::valarray<lbBase_t> &bodyForce,
+                      long long numNodesGlobal, int nSteps)
+    {
+        chimp_twophase_params p{};
+        p.tau0 = tau0;
+        p.tau1 = tau1;
+        p.sigma = sigma;
+        p.beta = beta;
+        p.momx = momx;
+        for (int d = 0; d < DXQY::nD; ++d) p.force[d] = bodyForce[d];
+        p.n_fluid_global = numNodesGlobal;
+        chimpCheck(chimp_step_twophase(h_, &p, nSteps));
+    }
+    void downloadPhaseField(ScalarField &cgField) { chimpCheck(chimp_download_phase_field(h_, cgField.data())); }
+    lbBase_t lastFluxForce() { return chimp_last_flux_force(h_); }
     chimp_lattice *handle() { return h_; }
 
 private:

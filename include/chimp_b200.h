@@ -152,6 +152,17 @@ int chimp_step_twophase(chimp_lattice *, const chimp_twophase_params *, int n_st
 int chimp_download_phase_field(chimp_lattice *, double *cg_sca);
 double chimp_last_flux_force(chimp_lattice *);
 
+/* ---- on-device reductions for callers (the step either side of the path) ----
+ * chimp_flux_force: calcFluxForceCartDir (LBglobalforcing.h:8-33): 2*(fixed_flux - sum_n qSumC(f(field,n))[cart_dir] / N)
+ * over the own nodes of all ranks (fixed-shape tree sum on the device, all-reduce callback across ranks).
+ * chimp_node_list_flux: out[bin[k]] += vel(0, component, nodes[k]) * rho(field, nodes[k]) in list order -- the
+ * mass flux through the pressure-boundary nodes (std_one_phase/main.cpp:607-619, bin = fluid phase, component = 2);
+ * uses the moments of the last step of the previous chimp_step_* call; only the products of the listed nodes
+ * cross the bus.  nodes are reference labels. */
+int chimp_flux_force(chimp_lattice *, int field_no, int cart_dir, double fixed_flux, long long n_nodes_global, double *force_out);
+int chimp_node_list_flux(chimp_lattice *, int n_list, const int32_t *nodes, const int32_t *bin, int n_bins, int field_no,
+                         int component, double *out);
+
 /* ---- halo plumbing for N ranks (replaces MonLatMpi::communicateLbField, LBmonlatmpi.h:236-297).
  * The engine packs outgoing populations into per-neighbour device buffers and unpacks
  * incoming ones; the transport (NCCL send/recv or peer stores) is supplied by the host. */

@@ -462,3 +462,50 @@ def test_peer_halos_bit_exact_vs_reference(name):
         for r, (lat, t) in enumerate(zip(lats, tabs)):
             bulk = t.bulk_nodes()
             assert np.array_equal(lat.download()[bulk], g.f(r, step)[bulk]), "rank %d step %d" % (r, step)
+
+
+def test_mass_flux_through_pressure_nodes_and_flux_force():
+    """the reductions a main performs either side of the path, formed on the device.
+    Mass flux (std_one_phase/main.cpp:607-619): products on the GPU, added in list order on the host --
+    bit-identical to the same loop over the downloaded fields, and equal to the reference's dump within the
+    tolerance of the tree-summed mass source.  Flux force (LBglobalforcing.h:8-33): tree sum vs sequential."""
+    g = helpers.Golden("onephase_d3q19_p1")
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    setup = helpers.one_phase_setup(g, lg, tabs)[0]
+    lat = build_engine_tables(g, lg, tabs, False)[0]
+    t = tabs[0]
+    lat.finalize(1)
+    lat.set_one_phase_attributes(setup["force_on"], setup["interior"], setup["add_source"], setup["scale"], g.args.get("rhow", 1.0))
+    lat.upload(setup["f0"])
+    step = int(max(g.dump))
+    lat.step_single(step, tau=g.args["tau"], force=g.force())
+    nodes, phase = setup["press_nodes"], setup["press_phase"]
+    assert len(nodes) > 0 and set(np.unique(phase)) <= {0, 1}
+    local, q, change = pkg.cases.one_phase_mass_flux(lat, setup)
+
+    def sequential(rho, vel):
+        acc = [0.0, 0.0]
+        for n, p in zip(nodes, phase):
+            acc[p] += vel[n, 2] * rho[n]
+        return np.array(acc)
+
+    assert np.array_equal(local, sequential(lat.download_rho()[:, 0], lat.download_vel()))
+    ref = sequential(g.rec(0, "step%d.rho" % step), g.rec(0, "step%d.vel" % step).reshape(t.size, -1))
+    assert np.allclose(local, ref, rtol=1e-9, atol=1e-18)
+    assert np.array_equal(q, 0.5 * local)
+    # nodes that are not own nodes contribute the zero-initialised rows of the reference fields
+    assert np.array_equal(lat.node_list_flux([0, t.size - 1], [0, 1], 2), np.zeros(2))
+    with pytest.raises(pkg.capi.ChimpError):
+        lat.node_list_flux(nodes, phase + 5, 2)
+    # flux force: 2 * (fixed - mean of sum_q c_qd f_q)
+    f = lat.download()
+    bulk = t.bulk_nodes()
+    c = pkg.geometry.BASIS["D3Q19"]
+    for d in range(3):
+        mean = 0.0
+        for n in bulk:
+            mean += float(np.sum(f[n, 0, :] * c[:, d]))
+        want = 2 * (1e-5 - mean / len(bulk))
+        got = lat.flux_force(0, d, 1e-5, len(bulk))
+        assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300) + 1e-20

@@ -25,7 +25,7 @@ def build(app, link_engine):
     cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", out, src]
     if link_engine:
         cmd += ["-I/usr/local/cuda/include", "-L" + helpers.PKG_DIR, "-lchimp_b200", "-L/usr/local/cuda/lib64", "-lcudart",
-                "-Wl,-rpath," + helpers.PKG_DIR]
+                "-Wl,-rpath," + helpers.PKG_DIR, "-pthread"]
     subprocess.run(cmd, check=True)
     return out
 
@@ -96,3 +96,97 @@ def test_std_case_app_matches_reference(name, tmp_path):
         assert np.array_equal(f[bulk], g.f(r, step)[bulk, 0])
         assert np.array_equal(rho[bulk], g.rec(r, "step%d.rho" % step)[bulk])
         assert np.array_equal(vel[bulk], g.rec(r, "step%d.vel" % step).reshape(-1, 3)[bulk])
+
+
+def write_case_files(g, tabs, tmp_path, attributes):
+    """geometry files for the reference-format reader, written by the product's byte-identical .vtklb writer"""
+    for r, t in enumerate(tabs):
+        t.write_vtklb(str(tmp_path / ("tmp%d.vtklb" % r)), attributes)
+    return str(tmp_path / "tmp")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["onephase_d3q19_p1", "onephase_trt_d3q19_p2"])
+def test_std_one_phase_app_matches_reference(name, tmp_path):
+    """host/apps/std_one_phase.cpp (structure of std_one_phase/main.cpp on the C++ mirror + engine) against the
+    reference's loop; tolerances as in test_one_phase_vs_reference (tree-summed mass change)"""
+    exe = build("std_one_phase", link_engine=True)
+    g = helpers.Golden(name)
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    names = ("nodetags", "domains", "force", "interior_domains", "normal_x", "normal_y", "normal_z")
+    prefix = write_case_files(g, tabs, tmp_path, {k: g.attr(k) for k in names})
+    step = max(g.dump)
+    F = g.force()
+    coll = ("tausym %r\n  tauanti %r" % tuple(g.args["trt"])) if "trt" in g.args else ("tau %r" % g.args["tau"])
+    deck = tmp_path / "input.dat"
+    # the reference loop runs i = 0..max: max = step - 1 gives `step` iterations; one write interval
+    deck.write_text("<iterations>\n  max %d\n  write %d\n<end>\n<fluid>\n  %s\n  bodyforce %r %r %r\n  rhow %r\n<end>\n"
+                    % (step - 1, step - 1, coll, F[0], F[1], F[2], g.args.get("rhow", 1.0)))
+    out = tmp_path / "out.bin"
+    subprocess.run([exe, str(deck), prefix, "0", str(out), str(g.nranks)], check=True)
+    data = open(out, "rb").read()
+    p = 0
+    setup = helpers.one_phase_setup(g, lg, tabs)
+    flux = np.zeros(2)
+    for r, t in enumerate(tabs):
+        (sz,) = struct.unpack_from("<i", data, p); p += 4
+        assert sz == t.size
+        f = np.frombuffer(data, "<f8", sz * 19, p).reshape(sz, 19); p += 8 * sz * 19
+        rho = np.frombuffer(data, "<f8", sz, p); p += 8 * sz
+        vel = np.frombuffer(data, "<f8", sz * 3, p).reshape(sz, 3); p += 8 * sz * 3
+        (nl,) = struct.unpack_from("<i", data, p); p += 4
+        mass = np.frombuffer(data, "<f8", nl, p); p += 8 * nl
+        bulk = t.bulk_nodes()
+        assert np.allclose(f[bulk], g.f(r, step)[bulk, 0], rtol=1e-12, atol=0)
+        assert np.allclose(rho[bulk], g.rec(r, "step%d.rho" % step)[bulk], rtol=1e-12, atol=0)
+        assert np.allclose(mass, g.rec(r, "step%d.massChange" % step), rtol=1e-9, atol=1e-16)
+        gv = g.rec(r, "step%d.vel" % step).reshape(sz, 3)
+        gr = g.rec(r, "step%d.rho" % step)
+        for n, ph in zip(setup[r]["press_nodes"], setup[r]["press_phase"]):
+            flux[ph] += gv[n, 2] * gr[n]
+    assert p == len(data)
+    # the .flux file of main.cpp:620-630: the last block holds the fluxes after `step` iterations
+    lines = open(str(out) + ".flux").read().splitlines()
+    assert lines[-3] == "PLOT AT ITERATION: %d" % (step - 1)
+    q1 = float(lines[-2].split()[2]); q2 = float(lines[-1].split()[2])
+    assert np.allclose([q1, q2], 0.5 * flux, rtol=1e-5, atol=1e-12)   # printed with 6 significant digits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["twophase_d3q19_p1", "twophase_d3q19_p2", "twophase_d2q9_p1"])
+def test_twophase_app_matches_reference(name, tmp_path):
+    """host/apps/twophase.cpp against the reference's colour-gradient loop, one and two ranks (in-process
+    ranks: scalar halo of phi, all-reduced flux force, population halos of both fields)"""
+    exe = build("twophase", link_engine=True)
+    g = helpers.Golden(name)
+    lg, tabs = helpers.build_tables(g)
+    prefix = write_case_files(g, tabs, tmp_path, {k: g.attr(k) for k in ("rho0", "rho1", "wettability", "source")})
+    step = max(g.dump)
+    a, F = g.args, g.force()
+    nd = 2 if g.lattice == "D2Q9" else 3
+    nq = 9 if g.lattice == "D2Q9" else 19
+    deck = tmp_path / "input.dat"
+    deck.write_text("outdir test\n<iterations>\n  max %d\n  write %d\n<end>\n<fluid>\n  tau %r %r\n  sigma %r\n  beta %r\n  momx %r\n"
+                    "  bodyforce %s\n<end>\n" % (step - 1, step - 1, a["tau2"][0], a["tau2"][1], a["sigma"], a["beta"], a["momx"],
+                                                " ".join(repr(x) for x in F[:nd])))
+    out = tmp_path / "out.bin"
+    subprocess.run([exe, g.lattice, str(deck), prefix, "0", str(out), str(g.nranks)], check=True)
+    data = open(out, "rb").read()
+    p = 0
+    for r, t in enumerate(tabs):
+        (sz,) = struct.unpack_from("<i", data, p); p += 4
+        assert sz == t.size
+        f = np.frombuffer(data, "<f8", sz * 2 * nq, p).reshape(sz, 2, nq); p += 8 * sz * 2 * nq
+        rho = np.frombuffer(data, "<f8", sz * 2, p).reshape(sz, 2); p += 8 * sz * 2
+        vel = np.frombuffer(data, "<f8", sz * nd, p).reshape(sz, nd); p += 8 * sz * nd
+        cg = np.frombuffer(data, "<f8", sz, p); p += 8 * sz
+        bulk = t.bulk_nodes()
+        assert np.allclose(f[bulk], g.f(r, step, 2)[bulk], rtol=1e-12, atol=1e-300)
+        assert np.allclose(rho[bulk], g.rec(r, "step%d.rho" % step).reshape(-1, 2)[bulk], rtol=1e-12, atol=0)
+        assert np.allclose(cg[bulk], g.rec(r, "step%d.cg" % step)[bulk], rtol=1e-10, atol=1e-14)
+        assert np.allclose(vel[bulk], g.rec(r, "step%d.vel" % step).reshape(sz, -1)[bulk], rtol=1e-9, atol=1e-16)
+    assert p == len(data)
+    last = open(str(out) + ".force.dat").read().splitlines()[-1].split()
+    fx = float(g.rec(0, "step%d.forceX" % step)[0])
+    assert int(last[0]) == step - 1 and abs(float(last[1]) - fx) <= 1e-10 * abs(fx)
