@@ -1,7 +1,7 @@
 // std_case on the B200 engine: the structure of the reference's src/std_case/main.cpp:17-160 with
 // the per-node loop, swapData, communicateLbField and bounceBackBnd.apply replaced by one call.
 //
-//   std_case <lattice D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess]
+//   std_case <lattice D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess [vtk dir]]
 //
 // Reads the same files as the reference main (input deck, <prefix><rank>.vtklb), runs
 // iterations/max iterations and writes raw f (LbField layout), rho and vel for the parity tests.
@@ -27,7 +27,7 @@ struct Rank {
 };
 
 template <typename LT>
-int run(const std::string &inputFile, const std::string &prefix, int firstRank, const std::string &outFile, int nRanks)
+int run(const std::string &inputFile, const std::string &prefix, int firstRank, const std::string &outFile, int nRanks, const std::string &vtkDir)
 {
     Input input(inputFile);
     const int nIterations = input["iterations"]["max"];
@@ -106,6 +106,15 @@ int run(const std::string &inputFile, const std::string &prefix, int firstRank, 
         std::fwrite(R.vel->data(), sizeof(double), std::size_t(sz) * LT::nD, fp);
     }
     std::fclose(fp);
+    if (!vtkDir.empty()) // OUTPUT VTK (std_case/main.cpp:101-104, 149-151)
+        for (int r = 0; r < nRanks; ++r) {
+            Rank<LT> &R = ranks[r];
+            Output<LT> output(*R.grid, R.bulkNodes, vtkDir, firstRank + r, nRanks);
+            output.add_file("lb_run");
+            output.add_scalar_variables({"rho"}, {*R.rho});
+            output.add_vector_variables({"vel"}, {*R.vel});
+            output.write(nIterations);
+        }
     std::cout << "std_case: " << nIterations << " iterations on " << nRanks << " rank(s) done" << std::endl;
     return 0;
 }
@@ -113,14 +122,15 @@ int run(const std::string &inputFile, const std::string &prefix, int firstRank, 
 int main(int argc, char **argv)
 {
     if (argc < 6) {
-        std::cout << "usage: std_case <D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess]" << std::endl;
+        std::cout << "usage: std_case <D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess [vtk output dir]]" << std::endl;
         return 2;
     }
     const std::string lattice = argv[1];
     const int rank = std::atoi(argv[4]);
     const int nRanks = argc > 6 ? std::atoi(argv[6]) : 1;
-    if (lattice == "D2Q9") return run<D2Q9>(argv[2], argv[3], rank, argv[5], nRanks);
-    if (lattice == "D3Q19") return run<D3Q19>(argv[2], argv[3], rank, argv[5], nRanks);
-    if (lattice == "D3Q27") return run<D3Q27>(argv[2], argv[3], rank, argv[5], nRanks);
+    const std::string vtkDir = argc > 7 ? argv[7] : "";
+    if (lattice == "D2Q9") return run<D2Q9>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
+    if (lattice == "D3Q19") return run<D3Q19>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
+    if (lattice == "D3Q27") return run<D3Q27>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
     chimp_host::die("unknown lattice " + lattice);
 }

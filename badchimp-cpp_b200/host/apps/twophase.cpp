@@ -2,7 +2,7 @@
 // (colour-gradient two-phase flow, two LbFields, flux-controlled body force) with the three node
 // loops, swapData, both ghost exchanges and bbBnd.apply replaced by GpuLattice::stepTwoPhase.
 //
-//   twophase <D2Q9|D3Q19> <input.dat> <vtklb prefix> <first rank> <out.bin> [nRanksInProcess]
+//   twophase <D2Q9|D3Q19> <input.dat> <vtklb prefix> <first rank> <out.bin> [nRanksInProcess [vtk dir]]
 //
 // Reads the reference's files (input deck with <iterations> max/write and <fluid> tau a b / sigma /
 // beta / momx / bodyforce, <prefix><rank>.vtklb with rho0 / rho1 / wettability attributes) and
@@ -28,7 +28,7 @@ struct Rank {
 };
 
 template <typename LT>
-int run(const std::string &inputFile, const std::string &prefix, int firstRank, const std::string &outFile, int nRanks)
+int run(const std::string &inputFile, const std::string &prefix, int firstRank, const std::string &outFile, int nRanks, const std::string &vtkDir)
 {
     Input input(inputFile);
     auto &fluid = input["fluid"];
@@ -123,6 +123,19 @@ int run(const std::string &inputFile, const std::string &prefix, int firstRank, 
         std::fwrite(R.cgField->data(), sizeof(double), sz, fp);
     }
     std::fclose(fp);
+    if (!vtkDir.empty()) // OUTPUT VTK (main_TWOPHASE.cpp:214-223, 424)
+        for (int r = 0; r < nRanks; ++r) {
+            Rank<LT> &R = ranks[r];
+            Output<LT> output(*R.grid, R.bulkNodes, vtkDir, firstRank + r, nRanks);
+            output.add_file("fluid");
+            output.add_scalar_variables({"rho"}, {*R.rho});
+            output.add_vector_variables({"vel"}, {*R.vel});
+            std::vector<int> geo(R.grid->size(), -1); // Nodes::geo (LBnodes.h:93-99)
+            for (int n = R.vtklb->beginNodeNo(); n < R.vtklb->endNodeNo(); ++n) geo[n] = R.nodes->isSolid(n) ? 1 : 0;
+            Output<LT, int> geoout(R.grid->pos(), vtkDir, firstRank + r, nRanks, "geo", geo);
+            geoout.write();
+            output.write(nIterations + 1);
+        }
     std::cout << "twophase: " << nIterations + 1 << " iterations on " << nRanks << " rank(s) done" << std::endl;
     return 0;
 }
@@ -130,13 +143,14 @@ int run(const std::string &inputFile, const std::string &prefix, int firstRank, 
 int main(int argc, char **argv)
 {
     if (argc < 6) {
-        std::cout << "usage: twophase <D2Q9|D3Q19> <input.dat> <vtklb prefix> <first rank> <out.bin> [nRanksInProcess]" << std::endl;
+        std::cout << "usage: twophase <D2Q9|D3Q19> <input.dat> <vtklb prefix> <first rank> <out.bin> [nRanksInProcess [vtk dir]]" << std::endl;
         return 2;
     }
     const std::string lattice = argv[1];
     const int rank = std::atoi(argv[4]);
     const int nRanks = argc > 6 ? std::atoi(argv[6]) : 1;
-    if (lattice == "D2Q9") return run<D2Q9>(argv[2], argv[3], rank, argv[5], nRanks);
-    if (lattice == "D3Q19") return run<D3Q19>(argv[2], argv[3], rank, argv[5], nRanks);
+    const std::string vtkDir = argc > 7 ? argv[7] : "";
+    if (lattice == "D2Q9") return run<D2Q9>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
+    if (lattice == "D3Q19") return run<D3Q19>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
     chimp_host::die("twophase needs D2Q9 or D3Q19 (D3Q27 has no colour-gradient weights)");
 }

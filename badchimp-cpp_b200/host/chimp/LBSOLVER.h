@@ -11,4 +11,5 @@
 #include "LBgpu.h"
 #include "LBranks.h"
 #include "Input.h"
+#include "Output.h"
 #endif

@@ -44,6 +44,9 @@ public:
     int getNumNodes() const { return nNodes_; }
     int size() const { return nNodes_; }
     lbBase_t *data() { return &data_[0]; }
+    const lbBase_t *data() const { return &data_[0]; }
+    int index(int fieldNo, int /*dimNo*/, int nodeNo) const { return nFields_ * nodeNo + fieldNo; } // LBfield.h:69-70
+    constexpr int dim() const { return 1; }
     void writeToFile(const std::string &fileName) const { chimp_host::writeRaw(fileName + ".lbsca", {nFields_, nNodes_}, &data_[0], data_.size()); }
     void readFromFile(const std::string &fileName) { chimp_host::readRaw(fileName + ".lbsca", {nFields_, nNodes_}, &data_[0], data_.size()); }
 
@@ -76,6 +79,9 @@ public:
     int num_fields() const { return nFields_; }
     int getNumNodes() const { return nNodes_; }
     lbBase_t *data() { return &data_[0]; }
+    const lbBase_t *data() const { return &data_[0]; }
+    int index(int fieldNo, int dimNo, int nodeNo) const { return nFields_ * DXQY::nD * nodeNo + DXQY::nD * fieldNo + dimNo; } // LBfield.h:219-220
+    constexpr int dim() const { return DXQY::nD; }
     void writeToFile(const std::string &fileName) const { chimp_host::writeRaw(fileName + ".lbvec", {nFields_, DXQY::nD, nNodes_}, &data_[0], data_.size()); }
     void readFromFile(const std::string &fileName) { chimp_host::readRaw(fileName + ".lbvec", {nFields_, DXQY::nD, nNodes_}, &data_[0], data_.size()); }
 

@@ -36,6 +36,15 @@ public:
     }
     int size() const { return nNodes_; }
     const std::vector<int> &neighborList() const { return neigList_; }
+    // all positions (nD ints per node, dummy node 0 first) and the positions of a node list (LBgrid.h:112-114)
+    const std::vector<int> &pos() const { return pos_; }
+    std::vector<int> pos(const std::vector<int> &nodes) const
+    {
+        std::vector<int> v(nodes.size() * DXQY::nD);
+        for (std::size_t n = 0; n < nodes.size(); ++n)
+            for (int d = 0; d < DXQY::nD; ++d) v[n * DXQY::nD + d] = pos_[std::size_t(nodes[n]) * DXQY::nD + d];
+        return v;
+    }
 
 private:
     int nNodes_;

@@ -35,7 +35,7 @@ DRIVER = os.path.join(HERE, "_ref", "ref_driver")
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attributes, keep_vtklb=False, checkpoint=False):
+def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attributes, keep_vtklb=False, checkpoint=False, vtk=False):
     d = tempfile.mkdtemp(prefix="golden_")
     os.makedirs(os.path.join(d, "out"))
     basis = lattice if lattice != "D3Q27" else G.BASIS["D3Q27"].astype(int)
@@ -48,6 +48,10 @@ def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attribu
            str(nranks), "--steps", str(steps), "--dump", ",".join(str(s) for s in dump)] + [str(a) for a in args]
     if checkpoint:
         cmd += ["--checkpoint", os.path.join(OUT, name + ".ckpt")]
+    if vtk:  # the reference's own Output<LT>::write (io/Output.h, io/VTK.h) after the last step
+        vdir = os.path.join(OUT, name + ".vtk")
+        shutil.rmtree(vdir, ignore_errors=True)
+        cmd += ["--vtk", vdir + "/"]
     subprocess.run(cmd, check=True, capture_output=True)
     gold = {"geo": np.asarray(geo, dtype=np.int32), "lattice": lattice, "periodic": periodic, "case": case,
             "steps": steps, "dump": np.array(dump), "args": np.array([str(a) for a in args]), "nranks": nranks}
@@ -108,9 +112,27 @@ def one_phase_attributes(shape, seed):
     return geo, attrs
 
 
+def vtk_goldens():
+    """small cases whose VTK files (written by the reference's Output class) are committed next to the dumps"""
+    shape = (6, 5, 7)
+    pack = G.sphere_pack(shape, 1.8, 0.7, 3).astype(int)
+    run_reference("vtk_std_d3q19_p2", G.z_slab_rank_map(pack, 2), "D3Q19", "xyz", "std_case", 3, [3],
+                  ["--tau", 0.8, "--force", "1e-5,2e-6,-3e-6"], {"init_rho": np.ones(shape)}, vtk=True)
+    pack2d = G.sphere_pack((9, 8), 2.0, 0.7, 9).astype(int)
+    x2 = np.arange(9)[:, None] * np.ones((9, 8))
+    r2 = (x2 < 4).astype(float)
+    run_reference("vtk_twophase_d2q9_p1", pack2d, "D2Q9", "xy", "twophase", 3, [3],
+                  ["--tau2", "1.0,1.0", "--sigma", 0.02, "--beta", 0.9, "--momx", 2e-5, "--force", "0,0,0"],
+                  {"rho0": r2, "rho1": 1.0 - r2, "wettability": 0.3 * (pack2d == 0), "source": np.zeros((9, 8), dtype=int)}, vtk=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+    if sys.argv[1:] == ["vtk"]:
+        vtk_goldens()
+        return
+    vtk_goldens()
     shape = (12, 10, 14)
     pack = G.sphere_pack(shape, 3.2, 0.62, 11).astype(int)
     ones = np.ones(shape)

@@ -32,6 +32,16 @@ typedef int MPI_Status;
 #define MPI_SUM 1
 #define MPI_MAX 2
 #define MPI_STATUS_IGNORE ((MPI_Status *)0)
+// io/VTK.h:100,1220,1288-1303 (parallel .pvtu piece records): MPI-IO on one node is positional POSIX I/O
+typedef int MPI_Info;
+typedef long long MPI_Offset;
+typedef struct { int fd; long long pos; } MPI_File;
+#define MPI_LONG 8
+#define MPI_CHAR 1
+#define MPI_MODE_APPEND 1
+#define MPI_MODE_WRONLY 2
+#define MPI_INFO_NULL 0
+#define MPI_SEEK_SET 0
 
 namespace mpishim {
 
@@ -145,5 +155,38 @@ inline int MPI_Barrier(MPI_Comm c)
     int a = 0, b = 0;
     return MPI_Allreduce(&a, &b, 1, MPI_INT, MPI_SUM, c);
 }
+
+inline int MPI_Initialized(int *flag) { *flag = 1; return 0; }
+
+// root's buffer to every rank: an all-reduce in which only the root contributes (bytes are OR-ed as
+// ints/doubles would not be exact for arbitrary payloads, so the payload travels through the mailbox)
+inline int MPI_Bcast(void *buf, int count, MPI_Datatype dt, int root, MPI_Comm c)
+{
+    const int me = mpishim::my_rank(), n = mpishim::world().nranks;
+    if (me == root) {
+        for (int r = 0; r < n; ++r)
+            if (r != root) MPI_Send(buf, count, dt, r, 9001, c);
+    } else {
+        MPI_Recv(buf, count, dt, root, 9001, c, MPI_STATUS_IGNORE);
+    }
+    return 0;
+}
+
+#include <fcntl.h>
+#include <unistd.h>
+inline int MPI_File_open(MPI_Comm, const char *name, int, MPI_Info, MPI_File *f)
+{
+    f->fd = ::open(name, O_WRONLY);
+    f->pos = 0;
+    return f->fd < 0;
+}
+inline int MPI_File_seek(MPI_File &f, MPI_Offset off, int) { f.pos = off; return 0; }
+inline int MPI_File_write(MPI_File &f, const void *buf, int count, MPI_Datatype dt, MPI_Status *)
+{
+    const ssize_t n = ::pwrite(f.fd, buf, (size_t)count * dt, f.pos);
+    f.pos += n > 0 ? n : 0;
+    return n < 0;
+}
+inline int MPI_File_close(MPI_File *f) { return ::close(f->fd); }
 
 #endif // ORACLE_MPI_SHIM_H

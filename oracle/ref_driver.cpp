@@ -53,6 +53,7 @@
 #include "lbsolver/LBinitiatefield.h"
 #include "lbsolver/LButilities.h"
 #include "lbsolver/LBvtk.h"
+#include "io/Output.h" // the reference's VTK writer, for the --vtk goldens
 #include "LBd3q27.h"
 
 namespace {
@@ -62,6 +63,7 @@ struct Opts {
     int nranks = 1, steps = 1;
     std::set<int> dumpSteps;
     bool dumpTables = true, dumpF = true, timing = false;
+    std::string vtk;        // directory for the reference's own Output<LT>::write() after the last step
     std::string checkpoint; // prefix for the reference's own writeToFile() dumps after the last step
     double tau = 0.8, tauSym = 0.0, tauAnti = 0.0; // TRT when tauSym > 0
     std::vector<double> force{0, 0, 0};
@@ -254,6 +256,16 @@ double runStdCase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid,
         f.writeToFile(p);
         rho.writeToFile(p);
         vel.writeToFile(p);
+    }
+    if (!o.vtk.empty()) { // std_case/main.cpp:101-104,149-151
+        int nProcs = 1;
+        MPI_Comm_size(MPI_COMM_WORLD, &nProcs);
+        std::vector<int> bulkNodes = bulk;
+        Output<LT> output(grid, bulkNodes, o.vtk, vtklb.getRank(), nProcs);
+        output.add_file("lb_run");
+        output.add_scalar_variables({"rho"}, {rho});
+        output.add_vector_variables({"vel"}, {vel});
+        output.write(o.steps);
     }
     return secs;
 }
@@ -530,6 +542,19 @@ double runTwoPhase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid
         bb.apply(1, f, grid);
         dump(i);
     }
+    if (!o.vtk.empty()) { // main_TWOPHASE.cpp:214-223,424
+        int nProcs = 1;
+        MPI_Comm_size(MPI_COMM_WORLD, &nProcs);
+        std::vector<int> bulkNodes = bulk;
+        Output<LT> output(grid, bulkNodes, o.vtk, vtklb.getRank(), nProcs);
+        output.add_file("fluid");
+        output.add_scalar_variables({"rho"}, {rho});
+        output.add_vector_variables({"vel"}, {vel});
+        auto geo = nodes.geo(grid, vtklb);
+        Output<LT, int> geoout(grid.pos(), o.vtk, vtklb.getRank(), nProcs, "geo", geo);
+        geoout.write();
+        output.write(o.steps);
+    }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
@@ -594,6 +619,7 @@ int main(int argc, char **argv)
         else if (a == "--no-f") o.dumpF = false;
         else if (a == "--time") o.timing = true;
         else if (a == "--checkpoint") o.checkpoint = next();
+        else if (a == "--vtk") o.vtk = next();
         else if (a == "--tau") o.tau = std::stod(next());
         else if (a == "--trt") { auto v = parseList(next()); o.tauSym = v[0]; o.tauAnti = v[1]; }
         else if (a == "--force") { auto v = parseList(next()); v.resize(3, 0.0); o.force = v; }

@@ -190,3 +190,56 @@ def test_twophase_app_matches_reference(name, tmp_path):
     last = open(str(out) + ".force.dat").read().splitlines()[-1].split()
     fx = float(g.rec(0, "step%d.forceX" % step)[0])
     assert int(last[0]) == step - 1 and abs(float(last[1]) - fx) <= 1e-10 * abs(fx)
+
+
+def _without_timestamp(data):
+    return b"\n".join(l for l in data.split(b"\n") if not l.startswith(b"<!-- Created"))
+
+
+def compare_vtk_tree(gold, mine):
+    n = 0
+    for root, _, files in os.walk(gold):
+        for f in files:
+            rel = os.path.relpath(os.path.join(root, f), gold)
+            a = open(os.path.join(gold, rel), "rb").read()
+            b = open(os.path.join(mine, rel), "rb").read()
+            if rel.endswith(".pvtu"):   # the header carries the wall-clock time of the run
+                a, b = _without_timestamp(a), _without_timestamp(b)
+            assert a == b, rel
+            n += 1
+    return n
+
+
+@pytest.mark.parametrize("name,nrho,fname,geo", [("vtk_std_d3q19_p2", 1, "lb_run", False), ("vtk_twophase_d2q9_p1", 2, "fluid", True)])
+def test_vtk_output_is_byte_identical_to_reference(name, nrho, fname, geo, tmp_path):
+    """Output<LT> of the host mirror writes the files the reference's Output/VTK classes write
+    (goldens produced by the reference's own io/Output.h through oracle/ref_driver --vtk): .vtu pieces with the
+    voxel / pixel mesh and raw appended arrays, .pvtu index with 100-byte piece records, 2 ranks and 2-D padding"""
+    exe = build("vtk_write", link_engine=False)
+    g = helpers.Golden(name)
+    lg, tabs = helpers.build_tables(g)
+    prefix = write_case_files(g, tabs, tmp_path, {k[5:]: g.z[k] for k in g.z.files if k.startswith("attr.")})
+    step = max(g.dump)
+    for r in range(g.nranks):
+        fb = tmp_path / ("fields%d.bin" % r)
+        fb.write_bytes(g.rec(r, "step%d.rho" % step).tobytes() + g.rec(r, "step%d.vel" % step).tobytes())
+        subprocess.run([exe, g.lattice, prefix, str(r), str(g.nranks), str(fb), str(nrho), str(tmp_path / "out"), fname, str(step)]
+                       + (["geo"] if geo else []), check=True)
+    assert compare_vtk_tree(os.path.join(helpers.GOLDEN, name + ".vtk"), str(tmp_path / "out")) >= 3
+
+
+@pytest.mark.gpu
+def test_std_case_app_writes_reference_vtk_files(tmp_path):
+    """engine -> download -> Output: the std_case application's VTK files equal the reference's byte for byte
+    (its populations and moments are bit-exact)"""
+    exe = build("std_case", link_engine=True)
+    g = helpers.Golden("vtk_std_d3q19_p2")
+    lg, tabs = helpers.build_tables(g)
+    prefix = write_case_files(g, tabs, tmp_path, {"init_rho": g.attr("init_rho")})
+    step = max(g.dump)
+    F = g.force()
+    deck = tmp_path / "input.dat"
+    deck.write_text("<iterations>\n  max %d\n  write %d\n<end>\n<fluid>\n  tau %r\n  bodyforce %r %r %r\n<end>\n"
+                    % (step, step, g.args["tau"], F[0], F[1], F[2]))
+    subprocess.run([exe, g.lattice, str(deck), prefix, "0", str(tmp_path / "out.bin"), str(g.nranks), str(tmp_path / "vtk")], check=True)
+    assert compare_vtk_tree(os.path.join(helpers.GOLDEN, g.name + ".vtk"), str(tmp_path / "vtk")) == 3
