@@ -109,18 +109,15 @@ __device__ __forceinline__ void staticFor(F &f)
     staticForImpl(f, std::make_integer_sequence<int, N>{});
 }
 
-// Resolves, for node i and every direction q, the address of f_q(i) in field 0 of the buffer
-// being read and hands it to fn(q, pointer).  `a` is any argument block with pl / nPad / idx
-// members.  Dead lanes (live == false) get the plane base and must not dereference it.
-template <class L, int IDX, class Args, class Fn>
-__device__ __forceinline__ void forEachSource(const Args &a, int i, bool live, Fn &&fn)
+// Resolves, for node i and every direction q, the slot s[q] with f_q(i) = in[q][s[q]] (kernel form: a bounce is
+// the out-of-plane slot i + bounceOff[q]).  `a` is any argument block with nPad / idx members.  Dead lanes
+// (live == false) get slot 0 and must not dereference it.
+template <class L, int IDX, class Args>
+__device__ __forceinline__ void resolveSources(const Args &a, int i, bool live, int (&s)[L::nQ])
 {
     if (IDX == IDX_TABLE) {
-        int src[L::nQ];
 #pragma unroll
-        for (int q = 0; q < L::nQ; ++q) src[q] = live ? __ldg(a.idx.table + ((unsigned)q * (unsigned)a.nPad + (unsigned)i)) : 0;
-#pragma unroll
-        for (int q = 0; q < L::nQ; ++q) fn(q, a.pl.in[q] + src[q]);
+        for (int q = 0; q < L::nQ; ++q) s[q] = live ? __ldg(a.idx.table + ((unsigned)q * (unsigned)a.nPad + (unsigned)i)) : 0;
     } else {
         constexpr int NW = (L::nQ + 3) / 4;
         const int tile = min(i >> 5, a.idx.nTiles - 1);
@@ -136,7 +133,6 @@ __device__ __forceinline__ void forEachSource(const Args &a, int i, bool live, F
             const int4 v = __ldg(bp + g);
             base[4 * g] = v.x; base[4 * g + 1] = v.y; base[4 * g + 2] = v.z; base[4 * g + 3] = v.w;
         }
-        int s[L::nQ];
         int anyRow = 0;
 #pragma unroll
         for (int q = 0; q < L::nQ; ++q) {
@@ -151,8 +147,18 @@ __device__ __forceinline__ void forEachSource(const Args &a, int i, bool live, F
                 if (base[q] < 0) s[q] = __ldg(a.idx.rows + (((unsigned)(-base[q] - 1) << 5) + lane));
         }
 #pragma unroll
-        for (int q = 0; q < L::nQ; ++q) fn(q, a.pl.in[q] + (live ? s[q] : 0));
+        for (int q = 0; q < L::nQ; ++q) s[q] = live ? s[q] : 0;
     }
+}
+
+// hands the address of f_q(i) in field 0 of the buffer being read to fn(q, pointer)
+template <class L, int IDX, class Args, class Fn>
+__device__ __forceinline__ void forEachSource(const Args &a, int i, bool live, Fn &&fn)
+{
+    int s[L::nQ];
+    resolveSources<L, IDX>(a, i, live, s);
+#pragma unroll
+    for (int q = 0; q < L::nQ; ++q) fn(q, a.pl.in[q] + s[q]);
 }
 
 template <class L, int IDX>
