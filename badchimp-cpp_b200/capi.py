@@ -54,7 +54,7 @@ SYMBOLS = [
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
-    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_node_list_flux", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
+    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
 ]
 
 
@@ -296,6 +296,12 @@ class Lattice:
         self._faces.append((send_src, recv_dst))
         _check(lib().chimp_add_halo_face(self.h, C.c_int(rank), C.c_longlong(len(send_src)), _p(send_src),
                                          C.c_longlong(len(recv_dst)), _p(recv_dst)))
+
+    def add_scalar_halo_face(self, k, send_src, recv_dst, send_ptr=None, recv_ptr=None):
+        send_src = np.ascontiguousarray(send_src, dtype=np.int64)
+        recv_dst = np.ascontiguousarray(recv_dst, dtype=np.int64)
+        _check(lib().chimp_add_scalar_halo_face(self.h, C.c_int(k), C.c_longlong(len(send_src)), _p(send_src),
+                                                C.c_longlong(len(recv_dst)), _p(recv_dst), C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))
 
     def set_boundary_count(self, n):
         _check(lib().chimp_set_boundary_count(self.h, C.c_int(n)))

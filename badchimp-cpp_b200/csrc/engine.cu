@@ -87,6 +87,7 @@ struct Neighbor {
     long long *d_phiSendSrc = nullptr, *d_phiRecvDst = nullptr; // scalar (phi) halo: slots of the phi array
     double *d_phiSendBuf = nullptr, *d_phiRecvBuf = nullptr;
     long long phiSendCount = 0, phiRecvCount = 0;
+    bool ownPhiBufs = true; // false: caller-owned scalar halo buffers (chimp_add_scalar_halo_face)
     // peer halos (CUDA IPC): the neighbour's two population buffers and its arrival flag for my face
     double *peerX[2] = {nullptr, nullptr};
     unsigned long long *peerFlags = nullptr;
@@ -810,7 +811,8 @@ void chimp_destroy(chimp_lattice *c)
     for (auto &nb : c->nbrs) {
         freeDev(nb.d_peerDst); freeDev(nb.d_blockCounter);
         freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf);
-        freeDev(nb.d_phiSendSrc); freeDev(nb.d_phiRecvDst); freeDev(nb.d_phiSendBuf); freeDev(nb.d_phiRecvBuf);
+        freeDev(nb.d_phiSendSrc); freeDev(nb.d_phiRecvDst);
+        if (nb.ownPhiBufs) { freeDev(nb.d_phiSendBuf); freeDev(nb.d_phiRecvBuf); }
     }
     if (c->evBoundary) cudaEventDestroy(c->evBoundary);
     if (c->evHalo) cudaEventDestroy(c->evHalo);
@@ -1692,6 +1694,42 @@ int chimp_add_halo_face(chimp_lattice *c, int neig_rank, long long n_send, const
         CUDA_OK(cudaMalloc(&nb.d_recvBuf, (size_t)n_recv * c->nFields * sizeof(double)));
     }
     c->nbrs.push_back(std::move(nb));
+    return 0;
+}
+
+int chimp_add_scalar_halo_face(chimp_lattice *c, int k, long long n_send, const long long *send_src, long long n_recv,
+                               const long long *recv_dst, void *send_dev, void *recv_dev)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2 || !c->d_phi) return fail("scalar halos need a two-field lattice with its phi table set");
+    if (k < 0 || k >= (int)c->nbrs.size()) return fail("bad neighbour index");
+    if (n_send < 0 || n_recv < 0 || (n_send && !send_src) || (n_recv && !recv_dst)) return fail("bad scalar halo lists");
+    for (long long e = 0; e < n_send; ++e)
+        if (send_src[e] < 0 || send_src[e] >= c->n) return fail("scalar send slot %lld is not an own node", send_src[e]);
+    for (long long e = 0; e < n_recv; ++e)
+        if (recv_dst[e] < c->nPad || recv_dst[e] >= c->nPhi - 1) return fail("scalar receive slot %lld is not a ghost slot", recv_dst[e]);
+    CUDA_OK(cudaSetDevice(c->device));
+    Neighbor &nb = c->nbrs[k];
+    freeDev(nb.d_phiSendSrc); freeDev(nb.d_phiRecvDst);
+    if (nb.ownPhiBufs) { freeDev(nb.d_phiSendBuf); freeDev(nb.d_phiRecvBuf); }
+    nb.phiSendCount = n_send;
+    nb.phiRecvCount = n_recv;
+    nb.ownPhiBufs = !(send_dev || recv_dev);
+    if ((send_dev == nullptr) != (recv_dev == nullptr)) return fail("pass both scalar halo buffers or neither");
+    if (n_send) {
+        CUDA_OK(cudaMalloc(&nb.d_phiSendSrc, (size_t)n_send * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(nb.d_phiSendSrc, send_src, (size_t)n_send * sizeof(long long), cudaMemcpyHostToDevice));
+        if (nb.ownPhiBufs) CUDA_OK(cudaMalloc(&nb.d_phiSendBuf, (size_t)n_send * sizeof(double)));
+    }
+    if (n_recv) {
+        CUDA_OK(cudaMalloc(&nb.d_phiRecvDst, (size_t)n_recv * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(nb.d_phiRecvDst, recv_dst, (size_t)n_recv * sizeof(long long), cudaMemcpyHostToDevice));
+        if (nb.ownPhiBufs) CUDA_OK(cudaMalloc(&nb.d_phiRecvBuf, (size_t)n_recv * sizeof(double)));
+    }
+    if (!nb.ownPhiBufs) {
+        nb.d_phiSendBuf = (double *)send_dev;
+        nb.d_phiRecvBuf = (double *)recv_dev;
+    }
     return 0;
 }
 

@@ -95,7 +95,7 @@ def sphere_pack_slab(shape, radius, porosity, seed, z0, z1):
     return geo
 
 
-def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: bool = True):
+def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: bool = True, wall_phi_ext: torch.Tensor = None):
     """One rank of a z-slab decomposition (periodic in x, y; z neighbours are other ranks).
 
     fluid_ext: bool [nx, ny, nz + 2]: the rank's own slab plus one halo layer below (index 0) and
@@ -106,6 +106,14 @@ def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: boo
     Returns dict(table int32 [nQ, n_pad], labels int32 [n_pad], n, n_pad, n_halo, n_boundary,
     faces = {"down": (send_src, recv_dst), "up": (send_src, recv_dst)}) with int64 slot offsets
     q*stride + slot.  Message order of a face: directions ascending, receiver cells in C-order of (x, y).
+
+    With wall_phi_ext (double [nx, ny, nz + 2], the wall colour (rho0 - rho1)/(rho0 + rho1) at solid cells) the
+    colour-gradient tables of a two-field lattice are added: ptable int32 [nQ, n_pad] (phi slot of neighbor(q, n):
+    own slot, n_pad + k for wall cell k -- solid cells next to an own fluid cell, the reference's solid boundary
+    nodes -- then the ghost cells -- fluid cells of the two halo layers, lower layer first, C-order of (x, y) --
+    and the zero slot n_pad + n_extra), phi_extra double [n_extra] (wall colours, zeros for the ghosts) and
+    scalar_faces = {"down": (send_src, recv_dst), "up": (...)}: phi slots of my bottom / top layer in C-order,
+    which is the order the neighbour numbers its ghosts in (communciateScalarField, LBmonlatmpi.h:181-205).
     """
     basis = G.BASIS[lattice]
     nq, nd = basis.shape
@@ -177,8 +185,44 @@ def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: boo
     labels[:n] = (order + 1).to(torch.int32)
     cat = lambda l: torch.cat(l) if l else torch.zeros(0, dtype=torch.int64, device=dev)
     faces = {k: (cat(v[0]), cat(v[1])) for k, v in faces.items()}
-    return dict(table=table, labels=labels, n=n, n_pad=n_pad, n_halo=n_halo, n_boundary=n_boundary, faces=faces,
-                stride=stride)
+    out = dict(table=table, labels=labels, n=n, n_pad=n_pad, n_halo=n_halo, n_boundary=n_boundary, faces=faces,
+               stride=stride)
+    if wall_phi_ext is not None:
+        own_ext = fluid_ext.clone()
+        own_ext[:, :, 0] = False
+        own_ext[:, :, -1] = False
+        near = torch.zeros_like(own_ext)
+        for q in range(nq - 1):
+            cx, cy, cz = (int(v) for v in basis[q])
+            near |= torch.roll(own_ext, shifts=(cx, cy, cz), dims=(0, 1, 2))  # cell has an own fluid neighbour
+        wall = near & ~fluid_ext
+        ghost = fluid_ext & ~own_ext
+        ghost[:, :, 1:-1] = False
+        n_wall = int(wall.sum().item())
+        n_low, n_up = int(ghost[:, :, 0].sum().item()), int(ghost[:, :, -1].sum().item())
+        n_extra = n_wall + n_low + n_up
+        slot_ext = torch.full(fluid_ext.shape, n_pad + n_extra, dtype=torch.int32, device=dev)
+        slot_ext[:, :, 1:-1] = torch.where(own, slot_grid, slot_ext[:, :, 1:-1])
+        slot_ext[wall] = n_pad + torch.arange(n_wall, dtype=torch.int32, device=dev)
+        low_slots = n_pad + n_wall + torch.arange(n_low, dtype=torch.int32, device=dev)
+        up_slots = n_pad + n_wall + n_low + torch.arange(n_up, dtype=torch.int32, device=dev)
+        layer = slot_ext[:, :, 0]
+        layer[ghost[:, :, 0]] = low_slots
+        layer = slot_ext[:, :, -1]
+        layer[ghost[:, :, -1]] = up_slots
+        ptable = torch.full((nq, n_pad), n_pad + n_extra, dtype=torch.int32, device=dev)
+        ext_cells = (cells_by_slot // nz) * (nz + 2) + (cells_by_slot % nz) + 1   # flat index in the extended array
+        for q in range(nq):
+            cx, cy, cz = (-int(v) for v in basis[q])                              # value at pos + c_q
+            nb = torch.roll(slot_ext, shifts=(cx, cy, cz), dims=(0, 1, 2)) if (cx or cy or cz) else slot_ext
+            ptable[q, :n] = nb.reshape(-1)[ext_cells]
+            del nb
+        phi_extra = torch.zeros(max(n_extra, 1), dtype=torch.float64, device=dev)
+        phi_extra[:n_wall] = wall_phi_ext.to(dev).double()[wall]
+        out.update(ptable=ptable, n_extra=n_extra, phi_extra=phi_extra, scalar_faces={
+            "down": (slot_grid[:, :, 0][own[:, :, 0]].long(), low_slots.long()),
+            "up": (slot_grid[:, :, -1][own[:, :, -1]].long(), up_slots.long())})
+    return out
 
 
 def build_phi_table(fluid: torch.Tensor, wall_phi: torch.Tensor, lattice: str, periodic: str = "xyz"):

@@ -54,7 +54,8 @@ def attach_ring(lat, slab, rank, world, device):
     lat.add_halo_face((rank - 1) % world, faces["down"][0].cpu().numpy(), faces["down"][1].cpu().numpy())
     lat.add_halo_face((rank + 1) % world, faces["up"][0].cpu().numpy(), faces["up"][1].cpu().numpy())
     lat.set_boundary_count(slab["n_boundary"])
-    ring = RingHalo(rank, world, len(faces["down"][0]), len(faces["down"][1]), len(faces["up"][0]), len(faces["up"][1]), device)
+    nf = lat.n_fields   # a packed message holds the face of every LbField, field after field
+    ring = RingHalo(rank, world, nf * len(faces["down"][0]), nf * len(faces["down"][1]), nf * len(faces["up"][0]), nf * len(faces["up"][1]), device)
     lat.set_halo_buffers(0, ring.send_down.data_ptr(), ring.recv_down.data_ptr())
     lat.set_halo_buffers(1, ring.send_up.data_ptr(), ring.recv_up.data_ptr())
 
@@ -84,6 +85,39 @@ def attach_ring_peer(lat, slab, rank, world):
     lat.connect_peer(0, everyone[down]["field_stride"], 1, everyone[down]["recv_up"], handles=everyone[down]["handles"])
     lat.connect_peer(1, everyone[up]["field_stride"], 0, everyone[up]["recv_down"], handles=everyone[up]["handles"])
     dist.barrier()
+
+
+def attach_ring_twophase(lat, slab, rank, world, device):
+    """two-field lattice on a z-slab: population halos (attach_ring), the scalar halo of phi between the moment
+    and the collide pass (communciateScalarField, main_TWOPHASE.cpp:287) and the all-reduce of the momentum sum
+    (:299), all over torch.distributed (NCCL on GPUs) on the stream the engine hands to the callbacks."""
+    ring = attach_ring(lat, slab, rank, world, device)
+    sf = slab["scalar_faces"]
+    sring = RingHalo(rank, world, len(sf["down"][0]), len(sf["down"][1]), len(sf["up"][0]), len(sf["up"][1]), device)
+    lat.add_scalar_halo_face(0, sf["down"][0].cpu().numpy(), sf["down"][1].cpu().numpy(), sring.send_down.data_ptr(), sring.recv_down.data_ptr())
+    lat.add_scalar_halo_face(1, sf["up"][0].cpu().numpy(), sf["up"][1].cpu().numpy(), sring.send_up.data_ptr(), sring.recv_up.data_ptr())
+    cuda = device.type == "cuda"
+    scratch = torch.zeros(16, dtype=torch.float64, device=device)
+    rt = C.CDLL("libcudart.so") if cuda else None
+    if rt is not None:
+        rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+
+    def on_scalar(stream_ptr):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr)):
+            sring.exchange()
+
+    def on_allreduce(dev_ptr, count, stream_ptr):
+        # the engine's scalar lives in its own allocation: stage it through a torch tensor on the same stream
+        assert count <= scratch.numel()
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr)):
+            assert rt.cudaMemcpyAsync(scratch.data_ptr(), dev_ptr, 8 * count, 3, stream_ptr) == 0
+            dist.all_reduce(scratch[:count])
+            assert rt.cudaMemcpyAsync(dev_ptr, scratch.data_ptr(), 8 * count, 3, stream_ptr) == 0
+
+    lat.set_scalar_exchange_callback(on_scalar)
+    lat.set_allreduce_callback(on_allreduce)
+    lat._sring, lat._scratch = sring, scratch
+    return ring
 
 
 def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):

@@ -179,6 +179,12 @@ void *chimp_halo_stream(chimp_lattice *);
  * their order defines the packed message.  The same rank may own two faces (2-rank ring). */
 int chimp_add_halo_face(chimp_lattice *, int neig_rank, long long n_send, const long long *send_src,
                         long long n_recv, const long long *recv_dst);
+/* structured-ingest two-field lattices: the scalar (phi) halo of neighbour / face k (communciateScalarField,
+ * LBbndmpi.h:141-156 -> LBmonlatmpi.h:181-205): phi slots of the own nodes whose colour the neighbour needs, in
+ * message order, and the ghost phi slots (>= n_pad, as numbered in chimp_set_phi_table_dev) the incoming values
+ * go to.  send_dev / recv_dev: caller-owned device buffers for the transport (both or neither). */
+int chimp_add_scalar_halo_face(chimp_lattice *, int k, long long n_send, const long long *send_src, long long n_recv,
+                               const long long *recv_dst, void *send_dev, void *recv_dev);
 /* Peer halos: instead of pack -> host transport -> unpack, the engine stores the outgoing populations
  * directly into the neighbour GPU's halo-in slots over NVLink and publishes an arrival counter there
  * (fused into the halo-coupled part of the step; replaces MPI_Send/MPI_Recv of LBmonlatmpi.h:253-257).

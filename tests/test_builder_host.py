@@ -36,7 +36,7 @@ def build_engine_tables(g, lg, tabs, boundary_first):
     return lats
 
 
-CASES = [n for n in helpers.all_golden_names() if not n.startswith("twophase")]
+CASES = [n for n in helpers.all_golden_names() if helpers.Golden(n).case != "twophase"]
 
 
 @pytest.mark.parametrize("boundary_first", [False, True])

@@ -98,3 +98,68 @@ def test_sphere_pack_slab_equals_slices_of_full_pack():
     assert np.array_equal(ext[:, :, 1:-1], full)
     assert np.array_equal(ext[:, :, 0], full[:, :, -1]) and np.array_equal(ext[:, :, -1], full[:, :, 0])
     assert np.array_equal(ing.sphere_pack_slab((20, 18, 24), 4.0, 0.5, 3, 6, 12), full[:, :, 6:12])
+
+
+@pytest.mark.parametrize("cuts", [[0, 5, 12], [0, 4, 8, 12]])
+def test_slab_phi_tables_reference_the_same_cells_as_the_single_rank_table(cuts):
+    """two-phase z-slabs: for every own node and direction the phi slot (own node / wall cell with its colour /
+    ghost cell of a halo layer / zero slot) designates the same global cell as the undecomposed phi table; the
+    scalar halo lists pair the sender's layer with the receiver's ghost numbering (C-order of (x, y))"""
+    import importlib
+    import torch
+    pkg = helpers.load_package()
+    ingest = importlib.import_module("badchimp_cpp_b200.ingest")
+    shape = (10, 9, 12)
+    geo = pkg.geometry.sphere_pack(shape, 2.5, 0.6, 5).astype(bool)
+    wall = np.random.default_rng(1).random(shape) * 2 - 1
+    pt, n_x, pe = ingest.build_phi_table(torch.from_numpy(geo), torch.from_numpy(wall), "D3Q19", "xyz")
+    n = int(geo.sum())
+    n_pad = ((n + 31) // 32) * 32
+    gid = -np.ones(shape, dtype=np.int64)
+    gid[geo] = np.arange(n)
+    pt, pe = pt.numpy(), pe.numpy()
+
+    def single(i, q):
+        s = pt[q, i]
+        return ("f", int(s)) if s < n_pad else (("w", float(pe[s - n_pad])) if s < n_pad + n_x else ("z",))
+
+    sends, recvs = {}, {}
+    for r in range(len(cuts) - 1):
+        z0, z1 = cuts[r], cuts[r + 1]
+        idx = np.arange(z0 - 1, z1 + 1) % shape[2]
+        ext, wext = geo[:, :, idx], wall[:, :, idx]
+        slab = ingest.build_slab_tables(torch.from_numpy(ext), "D3Q19", True, torch.from_numpy(wext))
+        ptab, pex, npd, nex = slab["ptable"].numpy(), slab["phi_extra"].numpy(), slab["n_pad"], slab["n_extra"]
+        labels = slab["labels"].numpy()[:slab["n"]]
+        own = np.argwhere(ext[:, :, 1:-1])
+        low, up = np.argwhere(ext[:, :, 0]), np.argwhere(ext[:, :, -1])
+        n_wall = nex - len(low) - len(up)
+
+        def cell_of_slot(s):
+            x, y, zl = own[labels[s] - 1]
+            return int(gid[x, y, (z0 + zl) % shape[2]])
+
+        for slot in range(slab["n"]):
+            me = cell_of_slot(slot)
+            for q in range(19):
+                s = ptab[q, slot]
+                if s < npd:
+                    got = ("f", cell_of_slot(s))
+                elif s < npd + n_wall:
+                    got = ("w", float(pex[s - npd]))
+                elif s < npd + nex:
+                    g = s - npd - n_wall
+                    x, y = low[g] if g < len(low) else up[g - len(low)]
+                    got = ("f", int(gid[x, y, (z0 - 1) % shape[2] if g < len(low) else z1 % shape[2]]))
+                else:
+                    got = ("z",)
+                assert got == single(me, q), (r, slot, q)
+        sf = slab["scalar_faces"]
+        sends[r] = {k: [cell_of_slot(int(s)) for s in sf[k][0]] for k in ("down", "up")}
+        recvs[r] = {"down": [int(gid[x, y, (z0 - 1) % shape[2]]) for x, y in low], "up": [int(gid[x, y, z1 % shape[2]]) for x, y in up]}
+        assert list(sf["down"][1].numpy()) == list(range(npd + n_wall, npd + n_wall + len(low)))
+        assert list(sf["up"][1].numpy()) == list(range(npd + n_wall + len(low), npd + nex))
+    world = len(cuts) - 1
+    for r in range(world):   # what I send down is what rank-1 expects in its "up" ghosts, and vice versa
+        assert sends[r]["down"] == recvs[(r - 1) % world]["up"]
+        assert sends[r]["up"] == recvs[(r + 1) % world]["down"]
