@@ -54,7 +54,7 @@ SYMBOLS = [
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
-    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
+    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles_twophase", "chimp_local_pointers_twophase", "chimp_connect_peer_scalar", "chimp_connect_world", "chimp_host_scalar_halo_lists", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
 ]
 
 
@@ -187,6 +187,13 @@ class Lattice:
         dst = np.zeros(nr_f, dtype=np.int64)
         _check(lib().chimp_host_halo_lists(self.h, C.c_int(k), _p(src), _p(dst)))
         return rank.value, src, dst
+
+    def host_scalar_recv_slots(self, k):
+        """ghost phi slots of neighbour k, in the order its values arrive"""
+        ns, nr = self.scalar_neighbor_info(k)
+        dst = np.zeros(nr, dtype=np.int64)
+        _check(lib().chimp_host_scalar_halo_lists(self.h, C.c_int(k), None, _p(dst)))
+        return dst
 
     # ---- state --------------------------------------------------------------------------
     def upload(self, f_aos):
@@ -328,6 +335,30 @@ class Lattice:
         _check(lib().chimp_connect_peer(self.h, C.c_int(k), hb, C.c_int(1 if pointers is not None else 0), pp,
                                         C.c_longlong(peer_field_stride), C.c_int(peer_face), C.c_longlong(len(peer_dst)),
                                         _p(peer_dst)))
+
+    def ipc_handles_twophase(self):
+        buf = (C.c_ubyte * 128)()
+        _check(lib().chimp_ipc_handles_twophase(self.h, buf))
+        return bytes(buf)
+
+    def local_pointers_twophase(self):
+        out = (C.c_void_p * 2)()
+        _check(lib().chimp_local_pointers_twophase(self.h, out))
+        return [int(x) if x else 0 for x in out]
+
+    def connect_peer_scalar(self, k, peer_phi_dst, handle=None, pointer=None):
+        """scalar (phi) halo of face k over peer memory: the neighbour's phi array (IPC handle, or raw pointer when
+        both lattices live in this process) and the ghost slot each of my outgoing colours lands in"""
+        peer_phi_dst = np.ascontiguousarray(peer_phi_dst, dtype=np.int64)
+        hb = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        _check(lib().chimp_connect_peer_scalar(self.h, C.c_int(k), hb, C.c_int(1 if pointer is not None else 0),
+                                               C.c_void_p(pointer), C.c_longlong(len(peer_phi_dst)), _p(peer_phi_dst)))
+
+    def connect_world(self, rank, world, handles=None, pointers=None):
+        """mailboxes of all ranks (rank order) for the global momentum sum"""
+        hb = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles)) if handles is not None else None
+        pp = (C.c_void_p * world)(*pointers) if pointers is not None else None
+        _check(lib().chimp_connect_world(self.h, C.c_int(rank), C.c_int(world), hb, C.c_int(1 if pointers is not None else 0), pp))
 
     def plane_stride(self):
         return int(lib().chimp_plane_stride(self.h))

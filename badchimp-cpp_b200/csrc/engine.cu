@@ -35,6 +35,8 @@ __global__ void haloPushKernel(double *, const double *, const long long *, cons
                                unsigned *, unsigned long long *, unsigned long long);
 __global__ void waitFlagKernel(const unsigned long long *, unsigned long long);
 __global__ void tilePhiRangesKernel(const int32_t *, int, int, int, int, int4 *);
+__global__ void sumPushKernel(const double *, void *const *, int, int, int, unsigned long long);
+__global__ void sumWaitFoldKernel(const void *, int, int, unsigned long long, double, double, double *, double *);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *, int, long long);
 __global__ void kernelTableKernel(const int32_t *, int32_t *, int, int, int, int, long long);
@@ -46,6 +48,8 @@ namespace {
 
 thread_local std::string g_err;
 std::map<std::string, void *> g_ipcOpen; // CUDA IPC mappings of this process (kept until exit)
+int openIpc(const unsigned char *handle64, void **out);
+void preloadForPeerStepping(const chimp_lattice *c);
 std::atomic<long long> g_launches{0};
 
 int fail(const char *fmt, ...)
@@ -77,6 +81,10 @@ LatInfo latInfo(int id)
 }
 int revDir(const LatInfo &li, int q) { return q == li.nQ - 1 ? q : (q + li.nPairs) % (li.nQ - 1); }
 
+// one rank's contribution to a global sum, delivered into every rank's mailbox: value first, then its sequence number
+struct MailSlot { double value; unsigned long long seq; };
+constexpr int kMaxWorld = 64;
+
 struct Op { int kind, dn, dq, sn, sq; }; // kind 0 copy, 1 anti bounce back, 2 swap
 
 struct Neighbor {
@@ -95,6 +103,10 @@ struct Neighbor {
     long long peerFieldStride = 0;
     int peerFace = -1;
     unsigned *d_blockCounter = nullptr;
+    // scalar (phi) peer halo: the neighbour's phi array, the ghost slots my values go to, its arrival flags
+    double *peerPhi = nullptr;
+    long long *d_peerPhiDst = nullptr;
+    unsigned *d_phiBlockCounter = nullptr;
     double *d_sendBuf = nullptr, *d_recvBuf = nullptr;   // owned
     double *x_sendBuf = nullptr, *x_recvBuf = nullptr;   // caller-owned overrides (chimp_set_halo_buffers)
     double *sendBuf() const { return x_sendBuf ? x_sendBuf : d_sendBuf; }
@@ -163,6 +175,11 @@ struct chimp_lattice {
     void *exchangeUser = nullptr, *scalarExchangeUser = nullptr;
     unsigned long long *d_flags = nullptr; // arrival counters written by the neighbours, one per face (max 8)
     bool peerHalos = false;
+    // two-phase over peer memory: sum mailbox of every rank (world pointers on the device), my rank / world size
+    MailSlot *d_mail = nullptr;
+    MailSlot **d_peerMail = nullptr;
+    int worldRank = -1, worldSize = 0;
+    bool peerTwoPhase = false;
     chimp_allreduce_fn allreduce = nullptr;
     void *allreduceUser = nullptr;
     std::vector<std::vector<long long>> hPhiSendSrc, hPhiRecvDst;
@@ -200,8 +217,9 @@ int allocateState(chimp_lattice *c)
     CUDA_OK(cudaMalloc(&c->d_vel, (size_t)c->nPad * c->li.nD * sizeof(double)));
     CUDA_OK(cudaMemsetAsync(c->d_rho, 0, (size_t)c->nPad * c->nFields * sizeof(double), c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_vel, 0, (size_t)c->nPad * c->li.nD * sizeof(double), c->stream));
-    CUDA_OK(cudaMalloc(&c->d_flags, 8 * sizeof(unsigned long long)));
-    CUDA_OK(cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(unsigned long long), c->stream));
+    // arrival counters written by the neighbours: [0, 8) population faces, [8, 16) scalar (phi) faces
+    CUDA_OK(cudaMalloc(&c->d_flags, 16 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemsetAsync(c->d_flags, 0, 16 * sizeof(unsigned long long), c->stream));
     return 0;
 }
 
@@ -804,12 +822,13 @@ void chimp_destroy(chimp_lattice *c)
     freeDev(c->d_table); freeDev(c->d_ktable); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
     freeDev(c->d_rho); freeDev(c->d_vel); freeDev(c->d_flags); freeDev(c->d_slotOf);
+    freeDev(c->d_mail); freeDev(c->d_peerMail);
     freeDev(c->d_tpSeq); freeDev(c->d_tpDeps); freeDev(c->d_tpDone); freeDev(c->d_tpTicket); freeDev(c->d_tpMom);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
     for (auto &nb : c->nbrs) {
-        freeDev(nb.d_peerDst); freeDev(nb.d_blockCounter);
+        freeDev(nb.d_peerDst); freeDev(nb.d_blockCounter); freeDev(nb.d_peerPhiDst); freeDev(nb.d_phiBlockCounter);
         freeDev(nb.d_sendSrc); freeDev(nb.d_recvDst); freeDev(nb.d_sendBuf); freeDev(nb.d_recvBuf);
         freeDev(nb.d_phiSendSrc); freeDev(nb.d_phiRecvDst);
         if (nb.ownPhiBufs) { freeDev(nb.d_phiSendBuf); freeDev(nb.d_phiRecvBuf); }
@@ -1452,8 +1471,8 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     if (c->lattice == CHIMP_D3Q27) return fail("D3Q27 has no colour-gradient weights B[] (not defined by the reference)");
     if (!c->densitySet) return fail("call chimp_set_twophase_density first (wall colour, main_TWOPHASE.cpp:173-181)");
     const bool multi = !c->nbrs.empty();
-    if (multi && (!c->exchange || !c->scalarExchange || !c->allreduce))
-        return fail("N-rank twophase needs the exchange, scalar-exchange and allreduce callbacks");
+    if (multi && !c->peerTwoPhase && (!c->exchange || !c->scalarExchange || !c->allreduce))
+        return fail("N-rank twophase needs the exchange, scalar-exchange and allreduce callbacks (or peer connections)");
     if (p->n_fluid_global <= 0) return fail("n_fluid_global must be positive");
     CUDA_OK(cudaSetDevice(c->device));
     TwoPhaseArgs a{};
@@ -1484,11 +1503,40 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
         fillPlanes(c, a.pl);
         double *const foutBuf = c->d_f[c->cur ^ 1];
         const bool mom = (s == n_steps - 1);
+        if (multi && c->peerTwoPhase) {
+            // the halo-in slots read by the moment pass were stored by the neighbours during their previous step
+            for (size_t k = 0; k < c->nbrs.size(); ++k) {
+                waitFlagKernel<<<1, 1, 0, c->stream>>>(c->d_flags + k, (unsigned long long)c->steps);
+                ++g_launches;
+            }
+        }
         // passes A + C (:238-246, :292-299): rho0, rho1, phi and the local x-momentum sum
         phaseMoments(c, a, gridAll);
         fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)gridAll, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, multi ? 0 : 1);
         ++g_launches;
-        if (multi) {
+        if (multi && c->peerTwoPhase) {
+            // everything between the passes goes over peer memory: my momentum sum into every rank's mailbox, my
+            // boundary colours into the neighbours' ghost slots; then wait for theirs and fold the sums in rank order
+            const unsigned long long seq = (unsigned long long)c->steps + 1;
+            const int parity = (int)(c->steps & 1);
+            sumPushKernel<<<1, kMaxWorld, 0, c->stream>>>(c->d_fluxSum, (void *const *)c->d_peerMail, c->worldRank, c->worldSize, parity, seq);
+            ++g_launches;
+            for (size_t k = 0; k < c->nbrs.size(); ++k) {
+                Neighbor &nb = c->nbrs[k];
+                if (!nb.phiSendCount) continue;
+                haloPushKernel<<<(unsigned)((nb.phiSendCount + 255) / 256), 256, 0, c->stream>>>(
+                    nb.peerPhi, c->d_phi, nb.d_phiSendSrc, nb.d_peerPhiDst, (int)nb.phiSendCount, 1, 0, 0, nb.d_phiBlockCounter,
+                    nb.peerFlags + 8 + nb.peerFace, seq);
+                ++g_launches;
+            }
+            for (size_t k = 0; k < c->nbrs.size(); ++k)
+                if (c->nbrs[k].phiRecvCount) {
+                    waitFlagKernel<<<1, 1, 0, c->stream>>>(c->d_flags + 8 + k, seq);
+                    ++g_launches;
+                }
+            sumWaitFoldKernel<<<1, kMaxWorld, 0, c->stream>>>(c->d_mail, c->worldSize, parity, seq, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX);
+            ++g_launches;
+        } else if (multi) {
             // communciateScalarField(cgField) (:287) and MPI_Allreduce of the momentum sum (:299)
             for (auto &nb : c->nbrs)
                 if (nb.phiSendCount) {
@@ -1516,14 +1564,27 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
             twoPhaseCollide(c, a, mom);
             CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
             CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
-            packHalos(c, foutBuf);
-            if (c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
+            if (c->peerTwoPhase) {
+                // both fields of the outgoing faces straight into the neighbours' halo-in slots (LBmonlatmpi.h:253-257)
+                const long long fieldStride = (long long)c->li.nQ * c->stride;
+                const int outIdx = c->cur ^ 1;
+                for (auto &nb : c->nbrs)
+                    if (nb.sendCount) {
+                        haloPushKernel<<<(unsigned)((nb.sendCount + 255) / 256), 256, 0, c->haloStream>>>(
+                            nb.peerX[outIdx], foutBuf, nb.d_sendSrc, nb.d_peerDst, (int)nb.sendCount, c->nFields, fieldStride,
+                            nb.peerFieldStride, nb.d_blockCounter, nb.peerFlags + nb.peerFace, (unsigned long long)(c->steps + 1));
+                        ++g_launches;
+                    }
+            } else {
+                packHalos(c, foutBuf);
+                if (c->exchange(c->exchangeUser, (void *)c->haloStream)) return fail("exchange callback failed");
+            }
             if (c->nBoundary && c->nBoundary < c->n) {
                 a.begin = c->nBoundary;
                 a.end = c->n;
                 twoPhaseCollide(c, a, mom);
             }
-            unpackHalos(c, foutBuf);
+            if (!c->peerTwoPhase) unpackHalos(c, foutBuf);
             CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
             CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
         }
@@ -1763,19 +1824,8 @@ int chimp_connect_peer(chimp_lattice *c, int k, const unsigned char *peer_handle
         // both contexts live in this process (tests): the peer's device pointers are directly usable
         for (int j = 0; j < 3; ++j) ptrs[j] = peer_ptrs3[j];
     } else {
-        for (int j = 0; j < 3; ++j) {
-            // one mapping per handle and process (a 2-rank ring reaches the same peer through both faces)
-            const std::string key((const char *)peer_handles192 + 64 * j, 64);
-            auto it = g_ipcOpen.find(key);
-            if (it == g_ipcOpen.end()) {
-                cudaIpcMemHandle_t h;
-                memcpy(&h, peer_handles192 + 64 * j, 64);
-                void *p = nullptr;
-                CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-                it = g_ipcOpen.emplace(key, p).first;
-            }
-            ptrs[j] = it->second;
-        }
+        for (int j = 0; j < 3; ++j)
+            if (openIpc(peer_handles192 + 64 * j, &ptrs[j])) return 1;
     }
     nb.peerX[0] = (double *)ptrs[0];
     nb.peerX[1] = (double *)ptrs[1];
@@ -1794,6 +1844,165 @@ int chimp_connect_peer(chimp_lattice *c, int k, const unsigned char *peer_handle
     bool all = true;
     for (auto &x : c->nbrs) all = all && x.peerFlags != nullptr;
     c->peerHalos = all;
+    if (all) preloadForPeerStepping(c);
+    return 0;
+}
+
+extern "C++" {
+namespace {
+// one mapping per handle and process (a 2-rank ring reaches the same peer through both faces)
+int openIpc(const unsigned char *handle64, void **out)
+{
+    const std::string key((const char *)handle64, 64);
+    auto it = g_ipcOpen.find(key);
+    if (it == g_ipcOpen.end()) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        void *p = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        it = g_ipcOpen.emplace(key, p).first;
+    }
+    *out = it->second;
+    return 0;
+}
+int ensureMailbox(chimp_lattice *c)
+{
+    if (c->d_mail) return 0;
+    CUDA_OK(cudaMalloc(&c->d_mail, 2 * kMaxWorld * sizeof(MailSlot)));
+    CUDA_OK(cudaMemset(c->d_mail, 0, 2 * kMaxWorld * sizeof(MailSlot)));
+    return 0;
+}
+} // namespace
+} // extern "C++"
+
+extern "C++" {
+namespace {
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, and loading waits for
+// running kernels -- including an arrival-flag wait that only ends when the peer's push, issued after the load,
+// has run: a deadlock.  Every kernel a step may launch is therefore loaded before the first wait kernel exists.
+template <class K>
+void preloadKernel(K kernel)
+{
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, kernel);
+}
+template <class L, int IDX>
+void preloadStepKernels(bool twoField)
+{
+    preloadKernel(collideStreamKernel<L, COLL_BGK, false, false, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_BGK, false, true, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_TRT, false, false, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_TRT, false, true, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_BGK, true, false, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_BGK, true, true, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_TRT, true, false, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_TRT, true, true, IDX>);
+    preloadKernel(massChangeKernel<L, IDX>);
+    if constexpr (L::id != D3Q27::id) {
+        if (twoField) {
+            preloadKernel(phaseMomentsKernel<L, IDX>);
+            preloadKernel(twoPhaseCollideKernel<L, false, IDX>);
+            preloadKernel(twoPhaseCollideKernel<L, true, IDX>);
+        }
+    }
+}
+void preloadForPeerStepping(const chimp_lattice *c)
+{
+    const bool two = c->nFields == 2;
+    const bool compact = c->indexForm == CHIMP_INDEX_COMPACT;
+    switch (c->lattice) {
+    case CHIMP_D2Q9: compact ? preloadStepKernels<D2Q9, IDX_COMPACT>(two) : preloadStepKernels<D2Q9, IDX_TABLE>(two); break;
+    case CHIMP_D3Q19: compact ? preloadStepKernels<D3Q19, IDX_COMPACT>(two) : preloadStepKernels<D3Q19, IDX_TABLE>(two); break;
+    case CHIMP_D3Q27: compact ? preloadStepKernels<D3Q27, IDX_COMPACT>(two) : preloadStepKernels<D3Q27, IDX_TABLE>(two); break;
+    }
+    preloadKernel(haloPushKernel);
+    preloadKernel(waitFlagKernel);
+    preloadKernel(sumPushKernel);
+    preloadKernel(sumWaitFoldKernel);
+    preloadKernel(fluxForceKernel);
+    preloadKernel(massFinalizeKernel);
+    preloadKernel(haloPackKernel);
+    preloadKernel(haloUnpackKernel);
+    preloadKernel(fillKernel);
+}
+} // namespace
+} // extern "C++"
+
+int chimp_ipc_handles_twophase(chimp_lattice *c, unsigned char *out128)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2 || !c->d_phi) return fail("needs a two-field lattice with its phi table set");
+    CUDA_OK(cudaSetDevice(c->device));
+    if (ensureMailbox(c)) return 1;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    void *ptrs[2] = {c->d_phi, c->d_mail};
+    for (int k = 0; k < 2; ++k) {
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaIpcGetMemHandle(&h, ptrs[k]));
+        memcpy(out128 + 64 * k, &h, 64);
+    }
+    return 0;
+}
+
+int chimp_local_pointers_twophase(chimp_lattice *c, void **out2)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2 || !c->d_phi) return fail("needs a two-field lattice with its phi table set");
+    CUDA_OK(cudaSetDevice(c->device));
+    if (ensureMailbox(c)) return 1;
+    out2[0] = c->d_phi;
+    out2[1] = c->d_mail;
+    return 0;
+}
+
+int chimp_connect_peer_scalar(chimp_lattice *c, int k, const unsigned char *peer_phi_handle64, int same_process, void *peer_phi_ptr,
+                              long long n_dst, const long long *peer_phi_dst)
+{
+    if (check(c, true)) return 1;
+    if (k < 0 || k >= (int)c->nbrs.size() || k >= 8) return fail("bad neighbour index");
+    Neighbor &nb = c->nbrs[k];
+    if (!nb.peerFlags) return fail("connect the population halo of face %d first (chimp_connect_peer)", k);
+    if (n_dst != nb.phiSendCount) return fail("peer phi list has %lld entries, my scalar send list %lld", n_dst, nb.phiSendCount);
+    CUDA_OK(cudaSetDevice(c->device));
+    void *p = peer_phi_ptr;
+    if (!same_process && openIpc(peer_phi_handle64, &p)) return 1;
+    nb.peerPhi = (double *)p;
+    freeDev(nb.d_peerPhiDst);
+    if (n_dst) {
+        CUDA_OK(cudaMalloc(&nb.d_peerPhiDst, (size_t)n_dst * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(nb.d_peerPhiDst, peer_phi_dst, (size_t)n_dst * sizeof(long long), cudaMemcpyHostToDevice));
+    }
+    if (!nb.d_phiBlockCounter) {
+        CUDA_OK(cudaMalloc(&nb.d_phiBlockCounter, sizeof(unsigned)));
+        CUDA_OK(cudaMemset(nb.d_phiBlockCounter, 0, sizeof(unsigned)));
+    }
+    return 0;
+}
+
+int chimp_connect_world(chimp_lattice *c, int rank, int world, const unsigned char *mail_handles, int same_process, void *const *mail_ptrs)
+{
+    if (check(c, true)) return 1;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail("bad rank %d / world size %d (at most %d ranks)", rank, world, kMaxWorld);
+    CUDA_OK(cudaSetDevice(c->device));
+    if (ensureMailbox(c)) return 1;
+    std::vector<MailSlot *> ptrs(world, nullptr);
+    for (int w = 0; w < world; ++w) {
+        void *p = nullptr;
+        if (w == rank) p = c->d_mail;
+        else if (same_process) p = mail_ptrs[w];
+        else if (openIpc(mail_handles + 64 * (size_t)w, &p)) return 1;
+        ptrs[w] = (MailSlot *)p;
+    }
+    freeDev(c->d_peerMail);
+    CUDA_OK(cudaMalloc(&c->d_peerMail, (size_t)world * sizeof(MailSlot *)));
+    CUDA_OK(cudaMemcpy(c->d_peerMail, ptrs.data(), (size_t)world * sizeof(MailSlot *), cudaMemcpyHostToDevice));
+    c->worldRank = rank;
+    c->worldSize = world;
+    bool all = c->peerHalos;
+    for (auto &x : c->nbrs) all = all && x.peerPhi != nullptr;
+    c->peerTwoPhase = all;
+    if (!all) return fail("connect every face (chimp_connect_peer, chimp_connect_peer_scalar) before chimp_connect_world");
+    preloadForPeerStepping(c);
     return 0;
 }
 
@@ -1883,6 +2092,14 @@ int chimp_host_halo_lists(chimp_lattice *c, int k, long long *send_src, long lon
     if (k < 0 || k >= (int)c->nbrs.size()) return fail("bad neighbour index");
     if (!c->hSendSrc[k].empty()) memcpy(send_src, c->hSendSrc[k].data(), c->hSendSrc[k].size() * sizeof(long long));
     if (!c->hRecvDst[k].empty()) memcpy(recv_dst, c->hRecvDst[k].data(), c->hRecvDst[k].size() * sizeof(long long));
+    return 0;
+}
+int chimp_host_scalar_halo_lists(chimp_lattice *c, int k, long long *send_src, long long *recv_dst)
+{
+    if (!c || !c->hostBuilt) return fail("host tables not built");
+    if (k < 0 || k >= (int)c->hPhiSendSrc.size()) return fail("bad neighbour index");
+    if (send_src && !c->hPhiSendSrc[k].empty()) memcpy(send_src, c->hPhiSendSrc[k].data(), c->hPhiSendSrc[k].size() * sizeof(long long));
+    if (recv_dst && !c->hPhiRecvDst[k].empty()) memcpy(recv_dst, c->hPhiRecvDst[k].data(), c->hPhiRecvDst[k].size() * sizeof(long long));
     return 0;
 }
 double chimp_irregular_fraction(chimp_lattice *c)

@@ -75,6 +75,42 @@ __global__ void nodeFluxKernel(const int32_t *__restrict__ nodes, int count, con
     out[k] = s >= 0 ? velComp[s] * rho[s] : 0.0;
 }
 
+// Global sums over peer memory (replaces MPI_Allreduce of one double, main_TWOPHASE.cpp:299): every rank stores its
+// local sum into slot `rank` of every rank's mailbox (value, fence, sequence number) ...
+struct MailSlotDev { double value; unsigned long long seq; };
+__global__ void sumPushKernel(const double *localSum, void *const *peerMail, int rank, int world, int parity, unsigned long long seq)
+{
+    const int w = threadIdx.x;
+    if (w >= world) return;
+    MailSlotDev *slot = (MailSlotDev *)peerMail[w] + parity * 64 + rank;
+    *(volatile double *)&slot->value = *localSum;
+    __threadfence_system();
+    *(volatile unsigned long long *)&slot->seq = seq;
+}
+
+// ... and, once all `world` contributions of this step have arrived, adds them in rank order -- every rank
+// obtains the same bits -- and forms F_x = 2 (momx - sum / nGlobal) (main_TWOPHASE.cpp:301-308)
+__global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
+                                  double *sumOut, double *forceX)
+{
+    const MailSlotDev *slots = (const MailSlotDev *)mail + parity * 64;
+    const int w = threadIdx.x;
+    if (w < world) {
+        const volatile unsigned long long *f = &slots[w].seq;
+        while (*f < seq) __nanosleep(100);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < world; ++k) s += *(const volatile double *)&slots[k].value;
+        *sumOut = s;
+        double mean = s;
+        mean /= nGlobal;
+        *forceX = 2 * (momx - mean);
+    }
+}
+
 __global__ void tilePhiRangesKernel(const int32_t *__restrict__ ptable, int n, int nPad, int nQ, int window, int4 *out)
 {
     __shared__ int r[4];

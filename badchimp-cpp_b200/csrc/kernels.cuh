@@ -572,6 +572,10 @@ __global__ void haloPushKernel(double *peerX, const double *__restrict__ X, cons
                                long long peerFieldStride, unsigned *blockCounter, unsigned long long *peerFlag,
                                unsigned long long value);
 __global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect);
+// one double per rank summed over all ranks through peer memory (kernels.cu)
+__global__ void sumPushKernel(const double *localSum, void *const *peerMail, int rank, int world, int parity, unsigned long long seq);
+__global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
+                                  double *sumOut, double *forceX);
 
 // halo pack: buf[k] = X[src[k]] ; unpack: X[dst[k]] = buf[k]   (64-bit slot offsets)
 __global__ void haloPackKernel(double *__restrict__ buf, const double *__restrict__ X,

@@ -120,6 +120,33 @@ def attach_ring_twophase(lat, slab, rank, world, device):
     return ring
 
 
+def attach_ring_twophase_peer(lat, slab, rank, world):
+    """two-field lattice on a z-slab with every exchange over peer memory (CUDA IPC + NVLink): population faces
+    and phi faces are stored straight into the neighbours' arrays, the momentum sum goes through per-rank
+    mailboxes and is added in rank order on every GPU.  No NCCL call and no host callback inside a step;
+    torch.distributed only carries the one-time handshake."""
+    faces, sf = slab["faces"], slab["scalar_faces"]
+    down, up = (rank - 1) % world, (rank + 1) % world
+    lat.add_halo_face(down, faces["down"][0].cpu().numpy(), faces["down"][1].cpu().numpy())
+    lat.add_halo_face(up, faces["up"][0].cpu().numpy(), faces["up"][1].cpu().numpy())
+    lat.add_scalar_halo_face(0, sf["down"][0].cpu().numpy(), sf["down"][1].cpu().numpy())
+    lat.add_scalar_halo_face(1, sf["up"][0].cpu().numpy(), sf["up"][1].cpu().numpy())
+    lat.set_boundary_count(slab["n_boundary"])
+    h2 = lat.ipc_handles_twophase()
+    info = {"handles": lat.ipc_handles(), "phi": h2[:64], "mail": h2[64:], "field_stride": lat.nq * lat.plane_stride(),
+            "recv_down": faces["down"][1].cpu().numpy(), "recv_up": faces["up"][1].cpu().numpy(),
+            "phi_recv_down": sf["down"][1].cpu().numpy(), "phi_recv_up": sf["up"][1].cpu().numpy()}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, info)
+    # what I send down lands in the "up" face (index 1) of rank-1, what I send up in the "down" face (0) of rank+1
+    lat.connect_peer(0, everyone[down]["field_stride"], 1, everyone[down]["recv_up"], handles=everyone[down]["handles"])
+    lat.connect_peer(1, everyone[up]["field_stride"], 0, everyone[up]["recv_down"], handles=everyone[up]["handles"])
+    lat.connect_peer_scalar(0, everyone[down]["phi_recv_up"], handle=everyone[down]["phi"])
+    lat.connect_peer_scalar(1, everyone[up]["phi_recv_down"], handle=everyone[up]["phi"])
+    lat.connect_world(rank, world, handles=[e["mail"] for e in everyone])
+    dist.barrier()
+
+
 def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
     """bench.py --gpus N (N > 1): every rank owns one size^3 block of a size x size x (size N) pack"""
     from . import bench_impl as B

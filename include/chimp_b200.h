@@ -77,6 +77,8 @@ int chimp_build_host(chimp_lattice *, int boundary_first);
 int chimp_host_table_info(chimp_lattice *, long long *info6);
 int chimp_host_table(chimp_lattice *, int32_t *table, int32_t *labels, uint32_t *pmask);
 int chimp_host_halo_lists(chimp_lattice *, int k, long long *send_src, long long *recv_dst);
+/* the same for the scalar (phi) halo of a two-field lattice: phi slots sent / ghost phi slots received */
+int chimp_host_scalar_halo_lists(chimp_lattice *, int k, long long *send_src, long long *recv_dst);
 
 /* builds the device tables; index_form is CHIMP_INDEX_TABLE or CHIMP_INDEX_COMPACT.
  * boundary_first != 0 orders halo-coupled nodes first so that their step can overlap. */
@@ -200,6 +202,18 @@ int chimp_local_pointers(chimp_lattice *, void **out3);
 int chimp_connect_peer(chimp_lattice *, int k, const unsigned char *peer_handles192, int same_process,
                        void *const *peer_ptrs3, long long peer_field_stride, int peer_face, long long n_dst,
                        const long long *peer_dst);
+/* Two-phase lattices over peer memory: additionally the scalar halo of phi is stored into the neighbours' ghost slots
+ * and the momentum sum of the flux controller (MPI_Allreduce, main_TWOPHASE.cpp:299) travels through a mailbox every rank
+ * exports: chimp_ipc_handles_twophase gives 2 x 64-byte handles (phi array, mailbox); chimp_connect_peer_scalar (after
+ * chimp_connect_peer of the same face) takes the neighbour's phi handle (or pointer, same process) and, per entry of my
+ * scalar send list, the ghost phi slot of the neighbour it lands in; chimp_connect_world takes the mailbox handles
+ * (world x 64 bytes, or pointers) of all ranks in rank order.  The sums are added in rank order on every rank, so all
+ * ranks obtain identical bits.  Afterwards chimp_step_twophase needs no callbacks. */
+int chimp_ipc_handles_twophase(chimp_lattice *, unsigned char *out128);
+int chimp_local_pointers_twophase(chimp_lattice *, void **out2);
+int chimp_connect_peer_scalar(chimp_lattice *, int k, const unsigned char *peer_phi_handle64, int same_process, void *peer_phi_ptr,
+                              long long n_dst, const long long *peer_phi_dst);
+int chimp_connect_world(chimp_lattice *, int rank, int world, const unsigned char *mail_handles, int same_process, void *const *mail_ptrs);
 /* the first n_boundary slots hold the halo-coupled nodes: they are stepped and packed first */
 int chimp_set_boundary_count(chimp_lattice *, int n_boundary);
 typedef int (*chimp_exchange_fn)(void *user, void *stream);

@@ -63,7 +63,11 @@ def main():
         lat = capi.lattice_from_device_table("D3Q19", slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
                                              slab["labels"].data_ptr(), 2, capi.INDEX_COMPACT, local)
         lat.set_phi_table_dev(slab["ptable"].data_ptr(), slab["n_extra"], slab["phi_extra"].data_ptr())
-        multi.attach_ring_twophase(lat, slab, rank, world, dev)
+        tp_mode = os.environ.get("CHIMP_HALO", "peer")
+        if tp_mode == "peer":
+            multi.attach_ring_twophase_peer(lat, slab, rank, world)
+        else:
+            multi.attach_ring_twophase(lat, slab, rank, world, dev)
         own = ext[:, :, 1:-1]
         x = torch.arange(size, device=dev)[:, None, None].expand(own.shape)
         lab = slab["labels"][: slab["n"]].long() - 1
@@ -90,7 +94,7 @@ def main():
         mass = total(float(rho.sum()))
         if rank == 0:
             mlups = n_total * steps / (ms * 1e-3) / 1e6
-            print(json.dumps({"config": "twophase colour gradient D3Q19 sphere pack %d^3 on %d GPUs (configs[3]), z-slabs, NCCL halos" % (size, world),
+            print(json.dumps({"config": "twophase colour gradient D3Q19 sphere pack %d^3 on %d GPUs (configs[3]), z-slabs, %s" % (size, world, "peer-memory halos + mailbox sum (NVLink)" if tp_mode == "peer" else "NCCL halos + all-reduce"),
                               "n_gpus": world, "fluid_nodes": n_total, "steps": steps, "ms_per_step": ms / steps, "MLUPS": mlups,
                               "MLUPS_per_gpu": mlups / world, "B_alg": 624.0, "frac_of_measured_hbm_per_gpu": 624.0 * mlups * 1e6 / world / 1e9 / peak,
                               "halo_bytes_per_step_per_gpu": halo, "scaling": "strong",

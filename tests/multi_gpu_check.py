@@ -86,7 +86,10 @@ def main():
     lat = capi.lattice_from_device_table("D3Q19", slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
                                          slab["labels"].data_ptr(), 2, capi.INDEX_COMPACT, local)
     lat.set_phi_table_dev(slab["ptable"].data_ptr(), slab["n_extra"], slab["phi_extra"].data_ptr())
-    multi.attach_ring_twophase(lat, slab, rank, world, dev)
+    if os.environ.get("CHIMP_HALO", "peer") == "peer":
+        multi.attach_ring_twophase_peer(lat, slab, rank, world)
+    else:
+        multi.attach_ring_twophase(lat, slab, rank, world, dev)
     own = geo[:, :, rank * nzr:(rank + 1) * nzr]
     lab = slab["labels"][: slab["n"]].cpu().numpy()
     r0 = torch.from_numpy(rho0[:, :, rank * nzr:(rank + 1) * nzr][own][lab - 1]).to(dev)

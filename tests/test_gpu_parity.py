@@ -509,3 +509,52 @@ def test_mass_flux_through_pressure_nodes_and_flux_force():
         want = 2 * (1e-5 - mean / len(bulk))
         got = lat.flux_force(0, d, 1e-5, len(bulk))
         assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300) + 1e-20
+
+
+def test_twophase_two_ranks_over_peer_memory_vs_reference():
+    """2-rank colour-gradient run with every exchange over peer memory: phi faces and population faces stored into
+    the neighbour's arrays, momentum sum through the mailboxes (added in rank order), arrival counters instead of
+    callbacks.  Both contexts live in this process and connect through raw device pointers; separate processes
+    connect through CUDA IPC (tests/multi_gpu_check.py)."""
+    g = helpers.Golden("twophase_d3q19_p2")
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    setup = pkg.cases.two_phase_setup(lg, tabs, g.attr("rho0"), g.attr("rho1"), g.attr("wettability"))
+    lats = []
+    for r, t in enumerate(tabs):
+        lat = pkg.capi.Lattice.from_rank_tables(t, n_fields=2)
+        ss = t.send_side(tabs)
+        for k, nr in enumerate(t.neig_ranks):
+            lat.add_neighbor(nr, ss[k][0], ss[k][1], ss[k][2], t.recv_nodes[k], t.recv_ndir[k], t.recv_dirs[k])
+        lat.add_halfway_bb(*t.halfway_bb(t.bulk_nodes()))
+        lat.set_solid_boundary(setup[r]["solid_bnd"])
+        lat.finalize(1, True)
+        lat.set_twophase_density(setup[r]["rho"])
+        lat.upload(setup[r]["f0"])
+        lats.append(lat)
+    world = len(lats)
+    for r, lat in enumerate(lats):
+        for k in range(lat.num_neighbors()):
+            nr = lat.neighbor_info(k)[0]
+            other = lats[nr]
+            ko = [j for j in range(other.num_neighbors()) if other.neighbor_info(j)[0] == r][0]
+            lat.connect_peer(k, other.nq * other.plane_stride(), ko, other.recv_dst(ko), pointers=other.local_pointers())
+            lat.connect_peer_scalar(k, other.host_scalar_recv_slots(ko), pointer=other.local_pointers_twophase()[0])
+    for r, lat in enumerate(lats):
+        lat.connect_world(r, world, pointers=[l.local_pointers_twophase()[1] for l in lats])
+    a = g.args
+    n_global = sum(len(t.bulk_nodes()) for t in tabs)
+    done = 0
+    for step in [s for s in g.dump if s > 0]:
+        for _ in range(step - done):   # one step at a time so that the contexts advance together
+            for lat in lats:
+                lat.step_twophase(1, a["tau2"][0], a["tau2"][1], a["sigma"], a["beta"], a["momx"], g.force(), n_global)
+        done = step
+        for r, (lat, t) in enumerate(zip(lats, tabs)):
+            bulk = t.bulk_nodes()
+            assert np.allclose(lat.download()[bulk], g.f(r, step, 2)[bulk], rtol=1e-12, atol=1e-300), "rank %d step %d" % (r, step)
+            assert np.allclose(lat.download_rho()[bulk], g.rec(r, "step%d.rho" % step).reshape(-1, 2)[bulk], rtol=1e-12, atol=0)
+            assert np.allclose(lat.download_phase_field()[bulk], g.rec(r, "step%d.cg" % step)[bulk], rtol=1e-10, atol=1e-14)
+            fx = float(g.rec(r, "step%d.forceX" % step)[0])
+            assert abs(lat.last_flux_force() - fx) <= 1e-10 * abs(fx)
+    assert lats[0].last_flux_force() == lats[1].last_flux_force()   # rank-order sum: identical bits on every rank
