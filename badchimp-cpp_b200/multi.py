@@ -147,6 +147,22 @@ def attach_ring_twophase_peer(lat, slab, rank, world):
     dist.barrier()
 
 
+def balanced_cuts(my_layer_counts, world):
+    """z cut planes such that every rank owns (nearly) the same number of fluid nodes: my_layer_counts holds the
+    fluid nodes of each z-layer of this rank's equal-thickness slab (int64 tensor on the rank's device)"""
+    all_layers = [torch.zeros_like(my_layer_counts) for _ in range(world)]
+    dist.all_gather(all_layers, my_layer_counts)
+    cum = torch.cumsum(torch.cat(all_layers), 0).cpu().numpy()
+    targets = cum[-1] * np.arange(1, world) / world
+    cuts = [0]
+    for t in targets:
+        k = int(np.searchsorted(cum, t))          # cum[k-1] < t <= cum[k]
+        below = cum[k - 1] if k > 0 else 0
+        cuts.append(k if (t - below) < (cum[k] - t) else k + 1)
+    cuts.append(len(cum))
+    return cuts
+
+
 def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
     """bench.py --gpus N (N > 1): every rank owns one size^3 block of a size x size x (size N) pack"""
     from . import bench_impl as B
@@ -162,16 +178,7 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
         # cut planes chosen so that every rank owns the same number of fluid nodes (the step time is the
         # maximum over ranks; equal-thickness slabs of a random pack differ by several per cent)
         layers = torch.from_numpy(ext[:, :, 1:-1].reshape(-1, size).sum(axis=0).astype(np.int64)).to(device)
-        all_layers = [torch.zeros_like(layers) for _ in range(world)]
-        dist.all_gather(all_layers, layers)
-        cum = torch.cumsum(torch.cat(all_layers), 0).cpu().numpy()
-        targets = cum[-1] * np.arange(1, world) / world
-        cuts = [0]
-        for t in targets:
-            k = int(np.searchsorted(cum, t))          # cum[k-1] < t <= cum[k]
-            below = cum[k - 1] if k > 0 else 0
-            cuts.append(k if (t - below) < (cum[k] - t) else k + 1)
-        cuts.append(size * world)
+        cuts = balanced_cuts(layers, world)
         z0, z1 = cuts[rank], cuts[rank + 1]
         ext = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, z0 - 1, z1 + 1)
     slab = ingest.build_slab_tables(torch.from_numpy(ext).to(device).bool(), lattice, boundary_first=True)

@@ -57,6 +57,12 @@ def main():
         gshape = (size, size, size)
         cuts = [round(k * size / world) for k in range(world + 1)]
         z0, z1 = cuts[rank], cuts[rank + 1]
+        if os.environ.get("BALANCE", "1") == "1" and all(cuts[k + 1] - cuts[k] == cuts[1] for k in range(world)):
+            # the step time is the maximum over ranks: cut the slabs at equal fluid-node counts
+            own = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, z0, z1)
+            layers = torch.from_numpy(own.reshape(-1, z1 - z0).sum(axis=0).astype(np.int64)).to(dev)
+            cuts = multi.balanced_cuts(layers, world)
+            z0, z1 = cuts[rank], cuts[rank + 1]
         ext = torch.from_numpy(ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, z0 - 1, z1 + 1)).to(dev).bool()
         wall_phi = torch.zeros(ext.shape, dtype=torch.float64, device=dev)      # wettability 0.5: rho0 = rho1 at the wall
         slab = ingest.build_slab_tables(ext, "D3Q19", True, wall_phi)
@@ -97,7 +103,7 @@ def main():
             print(json.dumps({"config": "twophase colour gradient D3Q19 sphere pack %d^3 on %d GPUs (configs[3]), z-slabs, %s" % (size, world, "peer-memory halos + mailbox sum (NVLink)" if tp_mode == "peer" else "NCCL halos + all-reduce"),
                               "n_gpus": world, "fluid_nodes": n_total, "steps": steps, "ms_per_step": ms / steps, "MLUPS": mlups,
                               "MLUPS_per_gpu": mlups / world, "B_alg": 624.0, "frac_of_measured_hbm_per_gpu": 624.0 * mlups * 1e6 / world / 1e9 / peak,
-                              "halo_bytes_per_step_per_gpu": halo, "scaling": "strong",
+                              "halo_bytes_per_step_per_gpu": halo, "scaling": "strong", "slab_cuts": [int(x) for x in cuts],
                               "note": "host clock around %d steps, max over ranks; sum rho0 = %.6f; flux force %.3e" % (steps, mass, lat.last_flux_force())}), flush=True)
         lat.close()
     if "d3q27" in what:

@@ -180,5 +180,5 @@ def test_twophase_fused_step_equals_two_pass_step(lattice, shape, periodic, lead
     assert np.allclose(one[0], ref[0], rtol=1e-12, atol=1e-15)
     assert np.allclose(one[1], ref[1], rtol=1e-12, atol=1e-15)
     assert np.allclose(one[2], ref[2], rtol=1e-10, atol=1e-14)
-    assert np.allclose(one[3], ref[3], rtol=1e-9, atol=1e-16)
+    assert np.allclose(one[3], ref[3], rtol=1e-9, atol=1e-14)   # u = O(1e-4): first moments differ by rounding of f
     assert abs(one[4] - ref[4]) <= 1e-10 * abs(ref[4])
