@@ -219,6 +219,11 @@ def run_b200(args):
         host_vel = torch.empty((n + 1, 3), dtype=torch.float64, pin_memory=True)
         lib = capi.lib()
         p = lat._single_params(tau, force, None)
+        # one untimed cycle first (first-touch of the pinned pages by the copy engines), like the warm-up steps
+        capi._check(lib.chimp_upload_lbfield(lat.h, C.c_void_p(host_f.data_ptr())))
+        capi._check(lib.chimp_step_single(lat.h, C.byref(p), C.c_int(1)))
+        capi._check(lib.chimp_download_rho(lat.h, C.c_void_p(host_rho.data_ptr()), C.c_int(1)))
+        capi._check(lib.chimp_download_vel(lat.h, C.c_void_p(host_vel.data_ptr())))
         t0 = time.perf_counter()
         capi._check(lib.chimp_upload_lbfield(lat.h, C.c_void_p(host_f.data_ptr())))
         capi._check(lib.chimp_step_single(lat.h, C.byref(p), C.c_int(args.steps)))
@@ -228,7 +233,7 @@ def run_b200(args):
         e2e = {"value": n * args.steps / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": host_f.numel() * 8 / args.steps,
                "d2h_bytes_per_step": (host_rho.numel() + host_vel.numel()) * 8 / args.steps,
-               "cycle": "upload LbField (pinned host, reference AoS) + %d steps + download rho, vel; wall clock" % args.steps}
+               "cycle": "upload LbField (pinned host, reference AoS) + %d steps + download rho, vel; wall clock; one untimed cycle before" % args.steps}
         assert abs(float(host_rho[1:].mean()) - 1.0) < 1e-9
     except Exception as exc:  # pragma: no cover
         e2e = {"value": None, "unit": "MLUPS", "error": str(exc)}

@@ -49,6 +49,7 @@ namespace {
 thread_local std::string g_err;
 std::map<std::string, void *> g_ipcOpen; // CUDA IPC mappings of this process (kept until exit)
 int openIpc(const unsigned char *handle64, void **out);
+int labelRangeOf(chimp_lattice *c);
 void preloadForPeerStepping(const chimp_lattice *c);
 std::atomic<long long> g_launches{0};
 
@@ -765,6 +766,7 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
     if (index_form == CHIMP_INDEX_TABLE && buildKernelTable(c)) return 1;
     if (allocateState(c)) return 1;
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (labelRangeOf(c)) return 1; // row range of the host arrays, so that the first transfer does not pay for it
     c->finalized = true;
     return 0;
 }
@@ -809,6 +811,7 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
     if (index_form == CHIMP_INDEX_TABLE && buildKernelTable(c)) { chimp_destroy(c); return 1; }
     if (allocateState(c)) { chimp_destroy(c); return 1; }
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (labelRangeOf(c)) { chimp_destroy(c); return 1; }
     c->finalized = true;
     *out = c;
     return 0;
@@ -846,7 +849,11 @@ void chimp_destroy(chimp_lattice *c)
 // nodes 1..N first, so the range is normally exactly the bulk rows).  Transfers touch only that row
 // range; when it holds nothing but bulk rows (labelsContiguous) a download is a pure device->host copy,
 // otherwise the caller's rows are staged first so that non-bulk rows keep their content.
-static int labelRange(chimp_lattice *c)
+static int labelRange(chimp_lattice *c) { return labelRangeOf(c); }
+
+extern "C++" {
+namespace {
+int labelRangeOf(chimp_lattice *c)
 {
     if (c->labelMax >= 0) return 0;
     std::vector<int32_t> lab(c->n);
@@ -857,6 +864,29 @@ static int labelRange(chimp_lattice *c)
     c->labelMin = lo;
     c->labelMax = hi;
     c->labelsContiguous = (long long)hi - lo + 1 == c->n;
+    return 0;
+}
+} // namespace
+} // extern "C++"
+
+// Staging area for layout conversion: the population buffer that is NOT current holds the state of the previous
+// step, which nothing reads any more (the next step overwrites it), so transfers need no allocation.  Only when the
+// caller's row range is larger than that buffer (labels far from contiguous) a temporary allocation is made.
+struct Staging {
+    double *ptr = nullptr;
+    bool owned = false;
+    ~Staging() { if (owned) cudaFree(ptr); }
+};
+static int acquireStaging(chimp_lattice *c, size_t bytes, Staging &st)
+{
+    const size_t have = (size_t)c->nFields * c->li.nQ * (size_t)c->stride * sizeof(double);
+    // not with peer halos: the neighbours may already be storing the next step's populations into that buffer
+    if (bytes <= have && !c->peerHalos) {
+        st.ptr = c->d_f[c->cur ^ 1];
+        return 0;
+    }
+    CUDA_OK(cudaMalloc(&st.ptr, bytes));
+    st.owned = true;
     return 0;
 }
 
@@ -870,8 +900,9 @@ int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
     const size_t rowDoubles = (size_t)c->nFields * c->li.nQ;
     const size_t rows = (size_t)(c->labelMax - c->labelMin + 1);
     const size_t bytes = rows * rowDoubles * sizeof(double);
-    double *d_aos = nullptr;
-    CUDA_OK(cudaMalloc(&d_aos, bytes));
+    Staging st;
+    if (acquireStaging(c, bytes, st)) return 1;
+    double *d_aos = st.ptr;
     CUDA_OK(cudaMemcpyAsync(d_aos, f_aos + (size_t)c->labelMin * rowDoubles, bytes, cudaMemcpyHostToDevice, c->stream));
     const unsigned grid = (unsigned)((c->n + 255) / 256);
     double *X = c->d_f[c->cur];
@@ -884,7 +915,6 @@ int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
     ++g_launches;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_aos);
     return 0;
 }
 
@@ -898,8 +928,9 @@ int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
     const size_t rows = (size_t)(c->labelMax - c->labelMin + 1);
     const size_t bytes = rows * rowDoubles * sizeof(double);
     double *host = f_aos + (size_t)c->labelMin * rowDoubles;
-    double *d_aos = nullptr;
-    CUDA_OK(cudaMalloc(&d_aos, bytes));
+    Staging st;
+    if (acquireStaging(c, bytes, st)) return 1;
+    double *d_aos = st.ptr;
     if (!c->labelsContiguous) CUDA_OK(cudaMemcpyAsync(d_aos, host, bytes, cudaMemcpyHostToDevice, c->stream));
     const unsigned grid = (unsigned)((c->n + 255) / 256);
     const double *X = c->d_f[c->cur];
@@ -913,7 +944,6 @@ int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(host, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_aos);
     return 0;
 }
 
@@ -924,8 +954,9 @@ static int downloadPlanes(chimp_lattice *c, double *host, const double *planes, 
     const size_t rows = (size_t)(c->labelMax - c->labelMin + 1);
     const size_t bytes = rows * aosStride * sizeof(double);
     double *hostRows = host + (size_t)c->labelMin * aosStride;
-    double *d_aos = nullptr;
-    CUDA_OK(cudaMalloc(&d_aos, bytes));
+    Staging st;
+    if (acquireStaging(c, bytes, st)) return 1;
+    double *d_aos = st.ptr;
     // a full overwrite of the row range needs no staging; partial rows (aosStride > nComp) or
     // non-bulk rows inside the range keep the caller's content
     if (!c->labelsContiguous || nComp != aosStride) CUDA_OK(cudaMemcpyAsync(d_aos, hostRows, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -935,7 +966,6 @@ static int downloadPlanes(chimp_lattice *c, double *host, const double *planes, 
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(hostRows, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_aos);
     return 0;
 }
 

@@ -166,17 +166,20 @@ __global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks,
                                 double *sumOut, double *forceX, int finish)
 {
     __shared__ double sh[8];
-    // four independent accumulators per thread keep several loads in flight; the summation order is
-    // fixed by (thread, slot), so the result is deterministic
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    // sixteen independent accumulators per thread keep sixteen loads in flight (the kernel is one block and purely
+    // latency-bound); the summation order is fixed by (thread, slot), so the result is deterministic
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.0;
     int b = threadIdx.x;
-    for (; b + 3 * (int)blockDim.x < nBlocks; b += 4 * blockDim.x) {
-        v0 += partial[b];
-        v1 += partial[b + blockDim.x];
-        v2 += partial[b + 2 * blockDim.x];
-        v3 += partial[b + 3 * blockDim.x];
+    for (; b + 15 * (int)blockDim.x < nBlocks; b += 16 * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] += partial[b + k * blockDim.x];
     }
-    for (; b < nBlocks; b += blockDim.x) v0 += partial[b];
+    for (; b < nBlocks; b += blockDim.x) v[0] += partial[b];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += v[k + 8];
+    const double v0 = v[0] + v[4], v1 = v[1] + v[5], v2 = v[2] + v[6], v3 = v[3] + v[7];
     const double s = blockSum256((v0 + v1) + (v2 + v3), sh);
     if (threadIdx.x == 0) {
         *sumOut = s;

@@ -35,6 +35,41 @@ def test_ten_thousand_steps_match_the_oracle_bit_for_bit():
     assert np.array_equal(rho, ref.rho[bulk, 0]) and np.array_equal(vel, ref.vel[bulk])
 
 
+def test_twophase_ten_thousand_steps_within_north_star_tolerance():
+    """colour-gradient run of 10 000 steps against the oracle port (pinned bit for bit to the reference's dumps):
+    rho0, rho1, u and phi within 1e-10 as north_star asks -- the only arithmetic difference is the order in which the
+    flux controller's momentum sum is added up (tree on the GPU, sequential on the CPU)"""
+    pkg = helpers.load_package()
+    port = helpers.oracle_port()
+    shape = (12, 10, 11)
+    geo = pkg.geometry.sphere_pack(shape, 3.0, 0.62, 4).astype(int)
+    x = np.arange(shape[0])[:, None, None] * np.ones(shape)
+    rho0 = (x < shape[0] / 2).astype(float)
+    lg = pkg.geometry.LatticeGeometry(geo, "D3Q19", "xyz")
+    t = lg.all_ranks()[0]
+    s = pkg.cases.two_phase_setup(lg, [t], rho0, 1.0 - rho0, 0.4 * (geo == 0))[0]
+    bulk = t.bulk_nodes()
+    args = dict(tau0=1.0, tau1=0.8, sigma=0.01, beta=1.0, momx=1e-5, force=(0.0, 1e-7, 0.0))
+    lat = pkg.capi.Lattice.from_rank_tables(t, n_fields=2)
+    lat.add_halfway_bb(*t.halfway_bb(bulk))
+    lat.set_solid_boundary(s["solid_bnd"])
+    lat.finalize(pkg.capi.INDEX_COMPACT)
+    lat.set_twophase_density(s["rho"])
+    lat.upload(s["f0"])
+    lat.step_twophase(10000, args["tau0"], args["tau1"], args["sigma"], args["beta"], args["momx"], args["force"], len(bulk))
+    ref = port.PortRank(1, t.neigh, bulk, 2, t.halfway_bb(bulk))
+    ref.f[:] = s["f0"]
+    ref.rho[:] = s["rho"]
+    fx = ref.step_twophase(10000, s["solid_bnd"], args["tau0"], args["tau1"], args["sigma"], args["beta"], args["momx"],
+                           list(args["force"]), len(bulk))
+    assert np.allclose(lat.download_rho()[bulk], ref.rho[bulk], rtol=1e-10, atol=1e-13)
+    assert np.allclose(lat.download_vel()[bulk], ref.vel[bulk], rtol=1e-10, atol=1e-13)
+    assert np.allclose(lat.download_phase_field()[bulk], ref.cg.reshape(-1)[bulk], rtol=1e-10, atol=1e-13)
+    assert np.allclose(lat.download()[bulk], ref.f[bulk], rtol=1e-10, atol=1e-14)
+    assert abs(lat.last_flux_force() - fx) <= 1e-8 * abs(fx) + 1e-16
+    assert np.isfinite(ref.f[bulk]).all() and ref.rho[bulk].min() > -1e-12
+
+
 def test_poiseuille_channel_matches_analytic_profile():
     """D2Q9 SRT, periodic in x, walls at y = 0 and y = H+1, body force along x: the steady profile
     is u(y) = F/(2 nu) y' (H - y') with y' measured from the half-way wall; half-way bounce back
