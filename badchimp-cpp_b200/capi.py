@@ -54,7 +54,7 @@ SYMBOLS = [
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
-    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles_twophase", "chimp_local_pointers_twophase", "chimp_connect_peer_scalar", "chimp_connect_world", "chimp_host_scalar_halo_lists", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
+    "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_capillary_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles_twophase", "chimp_local_pointers_twophase", "chimp_connect_peer_scalar", "chimp_connect_world", "chimp_host_scalar_halo_lists", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
 ]
 
 
@@ -281,6 +281,13 @@ class Lattice:
         out = C.c_double(0.0)
         _check(lib().chimp_flux_force(self.h, C.c_int(field_no), C.c_int(cart_dir), C.c_double(fixed_flux),
                                       C.c_longlong(n_nodes_global), C.byref(out)))
+        return out.value
+
+    def capillary_force(self, cart_dir, sigma_cap_numb, nu0, nu1, n_nodes_global):
+        """calcCapNumbForceCartDir (LBglobalforcing.h:35-98)"""
+        out = C.c_double(0.0)
+        _check(lib().chimp_capillary_force(self.h, C.c_int(cart_dir), C.c_double(sigma_cap_numb), C.c_double(nu0), C.c_double(nu1),
+                                           C.c_longlong(n_nodes_global), C.byref(out)))
         return out.value
 
     def node_list_flux(self, nodes, bins, n_bins, field_no=0, component=2):

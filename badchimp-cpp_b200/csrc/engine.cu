@@ -30,6 +30,7 @@ __global__ void fluxForceKernel(const double *, int, double, double, double *, d
 __global__ void massFinalizeKernel(const double *, int, const double *, double *, double *);
 __global__ void fillKernel(double *p, double v, long long count);
 __global__ void invertLabelsKernel(const int32_t *, int, int32_t *);
+__global__ void foldRowsKernel(const double *, int, double *);
 __global__ void nodeFluxKernel(const int32_t *, int, const int32_t *, int, const double *, const double *, double *);
 __global__ void haloPushKernel(double *, const double *, const long long *, const long long *, int, int, long long, long long,
                                unsigned *, unsigned long long *, unsigned long long);
@@ -1695,6 +1696,60 @@ int chimp_flux_force(chimp_lattice *c, int field_no, int cart_dir, double fixed_
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(force_out, c->d_forceX + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C++" {
+namespace {
+template <class L>
+void launchCapNumberSums(chimp_lattice *c, const StepArgs &a, int cartDir, unsigned grid, double *partial)
+{
+    if (c->indexForm == CHIMP_INDEX_COMPACT) capNumberSumsKernel<L, IDX_COMPACT><<<grid, 256, 0, c->stream>>>(a, cartDir, c->d_rho, partial);
+    else capNumberSumsKernel<L, IDX_TABLE><<<grid, 256, 0, c->stream>>>(a, cartDir, c->d_rho, partial);
+    ++g_launches;
+}
+} // namespace
+} // extern "C++"
+
+int chimp_capillary_force(chimp_lattice *c, int cart_dir, double sigma_cap_numb, double nu0, double nu1, long long n_nodes_global,
+                          double *force_out)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2) return fail("the capillary-number force needs a two-field lattice (rho of both fluids)");
+    if (cart_dir < 0 || cart_dir >= c->li.nD) return fail("cartesian direction %d out of range", cart_dir);
+    if (n_nodes_global <= 0 || !force_out) return fail("bad arguments");
+    if (!c->nbrs.empty() && !c->allreduce) return fail("capillary-number force across ranks needs chimp_set_allreduce_callback (LBglobalforcing.h:78-81)");
+    CUDA_OK(cudaSetDevice(c->device));
+    const unsigned grid = (unsigned)((c->n + 255) / 256);
+    double *d_partial = nullptr, *d_sums = nullptr;
+    CUDA_OK(cudaMalloc(&d_partial, (size_t)4 * std::max(grid, 1u) * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_sums, 4 * sizeof(double)));
+    StepArgs a{};
+    a.stride = c->stride;
+    a.n = c->n;
+    a.nPad = c->nPad;
+    fillIndexView(c, a.idx);
+    fillPlanes(c, a.pl);
+    switch (c->lattice) {
+    case CHIMP_D2Q9: launchCapNumberSums<D2Q9>(c, a, cart_dir, grid, d_partial); break;
+    case CHIMP_D3Q19: launchCapNumberSums<D3Q19>(c, a, cart_dir, grid, d_partial); break;
+    case CHIMP_D3Q27: launchCapNumberSums<D3Q27>(c, a, cart_dir, grid, d_partial); break;
+    }
+    foldRowsKernel<<<4, 256, 0, c->stream>>>(d_partial, (int)grid, d_sums);
+    ++g_launches;
+    int rc = 0;
+    if (!c->nbrs.empty() && c->allreduce(c->allreduceUser, d_sums, 4, (void *)c->stream)) rc = fail("allreduce callback failed");
+    double h[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_sums, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_partial);
+    cudaFree(d_sums);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail("capillary-number sums failed: %s", cudaGetErrorString(e));
+    // LBglobalforcing.h:85-95
+    for (double &x : h) x /= (double)n_nodes_global;
+    *force_out = 2 * (sigma_cap_numb - (h[0] * nu0 + h[1] * nu1)) / (h[2] * nu0 + h[3] * nu1);
     return 0;
 }
 

@@ -191,6 +191,16 @@ __global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks,
     }
 }
 
+__global__ void foldRowsKernel(const double *__restrict__ partial, int nBlocks, double *out)
+{
+    __shared__ double sh[8];
+    const double *row = partial + (long long)blockIdx.x * nBlocks;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nBlocks; b += blockDim.x) v += row[b];
+    const double s = blockSum256(v, sh);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 // ---- index compression (IDX_COMPACT) ---------------------------------------------------
 // One warp per (tile, q): base = smallest non-bounce source of the tile; a pair whose
 // sources span more than 253 keeps an explicit row.

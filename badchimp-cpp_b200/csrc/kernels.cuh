@@ -405,6 +405,36 @@ __global__ void __launch_bounds__(256) momentumSumKernel(const StepArgs a, long 
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
+// Capillary-number controller (LBglobalforcing.h:35-98): per-block partial sums of
+//   phi0 * m, phi1 * m, phi0, phi1   with m = qSumC(f(0, n))[cartDir], phi_s = rho_s / (rho_0 + rho_1)
+// over the own nodes (the reference takes field 0 of f and the stored ScalarField rho); partial[k][block].
+template <class L, int IDX>
+__global__ void __launch_bounds__(256) capNumberSumsKernel(const StepArgs a, int cartDir, const double *__restrict__ rho2, double *partial)
+{
+    __shared__ double sh[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    double f[L::nQ];
+    Gather<L, IDX>::load(a, 0ll, live ? i : 0, live, f);
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) {
+        const double m = cartDir == 0 ? firstMoment<L, 0>(f) : (cartDir == 1 || L::nD == 2) ? firstMoment<L, 1>(f) : firstMoment<L, 2>(f);
+        const double rho0 = rho2[i], rho1 = rho2[(long long)a.nPad + i];
+        const double rhoTot = rho0 + rho1;
+        const double phi0 = rho0 / rhoTot, phi1 = rho1 / rhoTot;
+        v[0] = phi0 * m;
+        v[1] = phi1 * m;
+        v[2] = phi0;
+        v[3] = phi1;
+    }
+    for (int k = 0; k < 4; ++k) {
+        const double s = blockSum256(v[k], sh);
+        if (threadIdx.x == 0) partial[(long long)k * gridDim.x + blockIdx.x] = s;
+    }
+}
+// out[k] = sum of partial[k][0 .. nBlocks) in a fixed order; one 256-thread block per k
+__global__ void foldRowsKernel(const double *__restrict__ partial, int nBlocks, double *out);
+
 // Node-list products for callers (mass flux through the pressure nodes, std_one_phase/main.cpp:607-619):
 // out[k] = vel(component, node_k) * rho(field, node_k); the host adds them in list order like the reference.
 __global__ void invertLabelsKernel(const int32_t *__restrict__ label, int n, int32_t *__restrict__ slotOf);

@@ -104,6 +104,13 @@ public:
         chimpCheck(chimp_flux_force(h_, fieldNo, cartDir, fixedFlux, numNodesGlobal, &F));
         return F;
     }
+    // calcCapNumbForceCartDir (LBglobalforcing.h:35-98)
+    lbBase_t capNumbForceCartDir(int cartDir, lbBase_t sigmaCapNumb, lbBase_t nu0, lbBase_t nu1, int numNodesGlobal)
+    {
+        lbBase_t F = 0.0;
+        chimpCheck(chimp_capillary_force(h_, cartDir, sigmaCapNumb, nu0, nu1, numNodesGlobal, &F));
+        return F;
+    }
     // twophase: wall colour from rho(2,size) (main_TWOPHASE.cpp:173-181, 280-284), then nSteps iterations of :236-392
     void setTwoPhaseDensity(ScalarField &rho) { chimpCheck(chimp_set_twophase_density(h_, rho.data())); }
     void stepTwoPhase(lbBase_t tau0, lbBase_t tau1, lbBase_t sigma, lbBase_t beta, lbBase_t momx, const std::valarray<lbBase_t> &bodyForce,

@@ -162,6 +162,11 @@ double chimp_last_flux_force(chimp_lattice *);
  * uses the moments of the last step of the previous chimp_step_* call; only the products of the listed nodes
  * cross the bus.  nodes are reference labels. */
 int chimp_flux_force(chimp_lattice *, int field_no, int cart_dir, double fixed_flux, long long n_nodes_global, double *force_out);
+/* calcCapNumbForceCartDir (LBglobalforcing.h:35-98) on a two-field lattice: uniform force that fixes the capillary number,
+ * 2*(sigma_cap_numb - (<phi0 m> nu0 + <phi1 m> nu1)) / (<phi0> nu0 + <phi1> nu1), m = qSumC(f(0,n))[cart_dir],
+ * phi_s = rho_s/(rho_0+rho_1) from the moments of the last step, <.> = sum over all ranks' own nodes / n_nodes_global. */
+int chimp_capillary_force(chimp_lattice *, int cart_dir, double sigma_cap_numb, double nu0, double nu1, long long n_nodes_global,
+                          double *force_out);
 int chimp_node_list_flux(chimp_lattice *, int n_list, const int32_t *nodes, const int32_t *bin, int n_bins, int field_no,
                          int component, double *out);
 

@@ -558,3 +558,48 @@ def test_twophase_two_ranks_over_peer_memory_vs_reference():
             fx = float(g.rec(r, "step%d.forceX" % step)[0])
             assert abs(lat.last_flux_force() - fx) <= 1e-10 * abs(fx)
     assert lats[0].last_flux_force() == lats[1].last_flux_force()   # rank-order sum: identical bits on every rank
+
+
+def test_capillary_number_force_and_error_paths_of_the_caller_side_reductions():
+    """calcCapNumbForceCartDir (LBglobalforcing.h:35-98) as a device reduction against the same loop over the
+    downloaded fields; argument errors of the 8(f2) entry points"""
+    g = helpers.Golden("twophase_d3q19_p1")
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    t = tabs[0]
+    setup = pkg.cases.two_phase_setup(lg, tabs, g.attr("rho0"), g.attr("rho1"), g.attr("wettability"))[0]
+    lat = pkg.capi.Lattice.from_rank_tables(t, n_fields=2)
+    lat.add_halfway_bb(*t.halfway_bb(t.bulk_nodes()))
+    lat.set_solid_boundary(setup["solid_bnd"])
+    lat.finalize(1)
+    lat.set_twophase_density(setup["rho"])
+    lat.upload(setup["f0"])
+    a = g.args
+    bulk = t.bulk_nodes()
+    lat.step_twophase(5, a["tau2"][0], a["tau2"][1], a["sigma"], a["beta"], a["momx"], g.force(), len(bulk))
+    f, rho = lat.download(), lat.download_rho()
+    c = pkg.geometry.BASIS["D3Q19"]
+    nu0, nu1, sig = 1.0 / 6.0, 0.1, 0.01 * 1e-3
+    for d in range(3):
+        s = np.zeros(4)
+        for n in bulk:
+            m = float(np.sum(f[n, 0, :] * c[:, d]))
+            p0, p1 = rho[n, 0] / (rho[n, 0] + rho[n, 1]), rho[n, 1] / (rho[n, 0] + rho[n, 1])
+            s += [p0 * m, p1 * m, p0, p1]
+        s /= len(bulk)
+        want = 2 * (sig - (s[0] * nu0 + s[1] * nu1)) / (s[2] * nu0 + s[3] * nu1)
+        got = lat.capillary_force(d, sig, nu0, nu1, len(bulk))
+        assert abs(got - want) <= 1e-10 * abs(want) + 1e-18
+    for bad in (lambda: lat.capillary_force(3, sig, nu0, nu1, len(bulk)), lambda: lat.capillary_force(0, sig, nu0, nu1, 0),
+                lambda: lat.flux_force(2, 0, 1e-5, len(bulk)), lambda: lat.flux_force(0, 5, 1e-5, len(bulk)),
+                lambda: lat.node_list_flux([1, 2], [0, 1], 2, field_no=7), lambda: lat.node_list_flux([1, 2], [0, 1], 2, component=4),
+                lambda: lat.connect_world(0, 2, pointers=[0, 0]), lambda: lat.add_scalar_halo_face(0, [0], [0])):
+        with pytest.raises(pkg.capi.ChimpError):
+            bad()
+    one = pkg.capi.Lattice.from_rank_tables(t)
+    one.add_halfway_bb(*t.halfway_bb(t.fluid_bnd_nodes()))
+    one.finalize(1)
+    with pytest.raises(pkg.capi.ChimpError):
+        one.capillary_force(0, sig, nu0, nu1, len(bulk))     # one-field lattice
+    with pytest.raises(pkg.capi.ChimpError):
+        one.ipc_handles_twophase()
