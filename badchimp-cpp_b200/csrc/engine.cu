@@ -37,7 +37,10 @@ __global__ void haloPushKernel(double *, const double *, const long long *, cons
 __global__ void waitFlagKernel(const unsigned long long *, unsigned long long);
 __global__ void tilePhiRangesKernel(const int32_t *, int, int, int, int, int4 *);
 __global__ void sumPushKernel(const double *, void *const *, int, int, int, unsigned long long);
-__global__ void sumWaitFoldKernel(const void *, int, int, unsigned long long, double, double, double *, double *);
+__global__ void sumWaitFoldKernel(const void *, int, int, unsigned long long, double, double, double *, double *, const unsigned long long *,
+                                  unsigned, unsigned long long);
+__global__ void foldAndPushKernel(const double *, int, double *, void *const *, int, int, int, unsigned long long);
+__global__ void waitFlagsKernel(const unsigned long long *, unsigned, unsigned long long);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *, int, long long);
 __global__ void kernelTableKernel(const int32_t *, int32_t *, int, int, int, int, long long);
@@ -1341,16 +1344,16 @@ void launchPhaseMoments(chimp_lattice *c, const TwoPhaseArgs &a, unsigned gridAl
     ++g_launches;
 }
 template <class L>
-void launchTwoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom)
+void launchTwoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom, cudaStream_t st)
 {
     if (a.end <= a.begin) return;
     const unsigned grid = (unsigned)((a.end - a.begin + CHIMP_TP_BLOCK - 1) / CHIMP_TP_BLOCK);
     if (c->indexForm == CHIMP_INDEX_COMPACT) {
-        if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
-        else twoPhaseCollideKernel<L, false, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
+        if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
+        else twoPhaseCollideKernel<L, false, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
     } else {
-        if (mom) twoPhaseCollideKernel<L, true, IDX_TABLE><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
-        else twoPhaseCollideKernel<L, false, IDX_TABLE><<<grid, CHIMP_TP_BLOCK, 0, c->stream>>>(a);
+        if (mom) twoPhaseCollideKernel<L, true, IDX_TABLE><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
+        else twoPhaseCollideKernel<L, false, IDX_TABLE><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
     }
     ++g_launches;
 }
@@ -1359,10 +1362,11 @@ void phaseMoments(chimp_lattice *c, const TwoPhaseArgs &a, unsigned gridAll)
     if (c->lattice == CHIMP_D2Q9) launchPhaseMoments<D2Q9>(c, a, gridAll);
     else launchPhaseMoments<D3Q19>(c, a, gridAll);
 }
-void twoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom)
+void twoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom, cudaStream_t st = nullptr)
 {
-    if (c->lattice == CHIMP_D2Q9) launchTwoPhaseCollide<D2Q9>(c, a, mom);
-    else launchTwoPhaseCollide<D3Q19>(c, a, mom);
+    if (!st) st = c->stream;
+    if (c->lattice == CHIMP_D2Q9) launchTwoPhaseCollide<D2Q9>(c, a, mom, st);
+    else launchTwoPhaseCollide<D3Q19>(c, a, mom, st);
 }
 } // namespace
 } // extern "C++"
@@ -1530,28 +1534,44 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     c->tpMomValid = false;
     a.partial = c->d_fluxPartial;
     const unsigned gridAll = (unsigned)((c->n + 255) / 256);
+    // CHIMP_TRACE=1: phase durations on the main stream (moment pass / exchange + global sum / boundary collide /
+    // interior collide + halo completion), averaged over the call and printed per rank
+    const bool trace = getenv("CHIMP_TRACE") && atoi(getenv("CHIMP_TRACE")) == 1;
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        ev.push_back(e);
+    };
     for (int s = 0; s < n_steps; ++s) {
         fillPlanes(c, a.pl);
         double *const foutBuf = c->d_f[c->cur ^ 1];
         const bool mom = (s == n_steps - 1);
+        mark();
         if (multi && c->peerTwoPhase) {
             // the halo-in slots read by the moment pass were stored by the neighbours during their previous step
-            for (size_t k = 0; k < c->nbrs.size(); ++k) {
-                waitFlagKernel<<<1, 1, 0, c->stream>>>(c->d_flags + k, (unsigned long long)c->steps);
-                ++g_launches;
-            }
+            waitFlagsKernel<<<1, 32, 0, c->stream>>>(c->d_flags, (1u << c->nbrs.size()) - 1u, (unsigned long long)c->steps);
+            ++g_launches;
         }
+        mark();
         // passes A + C (:238-246, :292-299): rho0, rho1, phi and the local x-momentum sum
         phaseMoments(c, a, gridAll);
-        fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)gridAll, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, multi ? 0 : 1);
-        ++g_launches;
         if (multi && c->peerTwoPhase) {
-            // everything between the passes goes over peer memory: my momentum sum into every rank's mailbox, my
+            // fold of the partials and delivery of the local sum into every rank's mailbox in one launch
+            foldAndPushKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)gridAll, c->d_fluxSum, (void *const *)c->d_peerMail, c->worldRank,
+                                                         c->worldSize, (int)(c->steps & 1), (unsigned long long)c->steps + 1);
+        } else {
+            fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxPartial, (int)gridAll, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, multi ? 0 : 1);
+        }
+        ++g_launches;
+        mark();
+        if (multi && c->peerTwoPhase) {
+            // everything between the passes goes over peer memory: the momentum sums through the mailboxes (above), my
             // boundary colours into the neighbours' ghost slots; then wait for theirs and fold the sums in rank order
             const unsigned long long seq = (unsigned long long)c->steps + 1;
             const int parity = (int)(c->steps & 1);
-            sumPushKernel<<<1, kMaxWorld, 0, c->stream>>>(c->d_fluxSum, (void *const *)c->d_peerMail, c->worldRank, c->worldSize, parity, seq);
-            ++g_launches;
             for (size_t k = 0; k < c->nbrs.size(); ++k) {
                 Neighbor &nb = c->nbrs[k];
                 if (!nb.phiSendCount) continue;
@@ -1560,12 +1580,11 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
                     nb.peerFlags + 8 + nb.peerFace, seq);
                 ++g_launches;
             }
+            unsigned phiMask = 0;
             for (size_t k = 0; k < c->nbrs.size(); ++k)
-                if (c->nbrs[k].phiRecvCount) {
-                    waitFlagKernel<<<1, 1, 0, c->stream>>>(c->d_flags + 8 + k, seq);
-                    ++g_launches;
-                }
-            sumWaitFoldKernel<<<1, kMaxWorld, 0, c->stream>>>(c->d_mail, c->worldSize, parity, seq, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX);
+                if (c->nbrs[k].phiRecvCount) phiMask |= 1u << k;
+            sumWaitFoldKernel<<<1, kMaxWorld + 32, 0, c->stream>>>(c->d_mail, c->worldSize, parity, seq, p->momx, (double)p->n_fluid_global,
+                                                                  c->d_fluxSum, c->d_forceX, c->d_flags + 8, phiMask, seq);
             ++g_launches;
         } else if (multi) {
             // communciateScalarField(cgField) (:287) and MPI_Allreduce of the momentum sum (:299)
@@ -1584,17 +1603,29 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
             fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_fluxSum, 1, p->momx, (double)p->n_fluid_global, c->d_fluxSum, c->d_forceX, 1);
             ++g_launches;
         }
+        mark();
         // pass D (:312-376) + ghost exchange of both fields (:387-388)
         if (!multi) {
             a.begin = 0;
             a.end = c->n;
             twoPhaseCollide(c, a, mom);
+            mark();
         } else {
             a.begin = 0;
             a.end = c->nBoundary ? c->nBoundary : c->n;
-            twoPhaseCollide(c, a, mom);
-            CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
-            CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+            // peer mode: the halo-coupled nodes run on the high-priority halo stream, concurrently with the interior nodes
+            // (both read the old buffer and phi, and write disjoint slots); callback mode keeps them on the main stream
+            const bool split = c->peerTwoPhase && c->nBoundary && c->nBoundary < c->n;
+            if (split) {
+                CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
+                CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+                twoPhaseCollide(c, a, mom, c->haloStream);
+            } else {
+                twoPhaseCollide(c, a, mom);
+                CUDA_OK(cudaEventRecord(c->evBoundary, c->stream));
+                CUDA_OK(cudaStreamWaitEvent(c->haloStream, c->evBoundary, 0));
+            }
+            mark();
             if (c->peerTwoPhase) {
                 // both fields of the outgoing faces straight into the neighbours' halo-in slots (LBmonlatmpi.h:253-257)
                 const long long fieldStride = (long long)c->li.nQ * c->stride;
@@ -1619,10 +1650,28 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
             CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
             CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
         }
+        mark();
         c->cur ^= 1;
         ++c->steps;
     }
     CUDA_OK(cudaGetLastError());
+    if (trace && !ev.empty()) {
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        const int per = (int)ev.size() / n_steps; // marks per step: start, wait done, A done, exchange done, D(b) done, end
+        std::vector<double> sum(per, 0.0);
+        for (int s = 0; s < n_steps; ++s)
+            for (int k = 0; k + 1 < per; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[(size_t)s * per + k], ev[(size_t)s * per + k + 1]);
+                sum[k] += ms;
+            }
+        float total = 0.f;
+        cudaEventElapsedTime(&total, ev.front(), ev.back());
+        fprintf(stderr, "[chimp trace] rank %d: %d steps, %.4f ms/step; phases (ms/step):", c->worldRank, n_steps, total / n_steps);
+        for (int k = 0; k + 1 < per; ++k) fprintf(stderr, " %.4f", sum[k] / n_steps);
+        fprintf(stderr, "  [flag wait | moment pass + fold | phi + sum exchange | boundary collide | interior collide + halo]\n");
+        for (auto e : ev) cudaEventDestroy(e);
+    }
     return 0;
 }
 
@@ -2004,6 +2053,8 @@ void preloadForPeerStepping(const chimp_lattice *c)
     preloadKernel(waitFlagKernel);
     preloadKernel(sumPushKernel);
     preloadKernel(sumWaitFoldKernel);
+    preloadKernel(foldAndPushKernel);
+    preloadKernel(waitFlagsKernel);
     preloadKernel(fluxForceKernel);
     preloadKernel(massFinalizeKernel);
     preloadKernel(haloPackKernel);

@@ -88,16 +88,54 @@ __global__ void sumPushKernel(const double *localSum, void *const *peerMail, int
     *(volatile unsigned long long *)&slot->seq = seq;
 }
 
+// fold of the per-block partials (fixed order, as fluxForceKernel) and delivery of the local sum in one launch
+__global__ void foldAndPushKernel(const double *__restrict__ partial, int nBlocks, double *sumOut, void *const *peerMail, int rank,
+                                  int world, int parity, unsigned long long seq)
+{
+    __shared__ double sh[8];
+    __shared__ double total;
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.0;
+    int b = threadIdx.x;
+    for (; b + 15 * (int)blockDim.x < nBlocks; b += 16 * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] += partial[b + k * blockDim.x];
+    }
+    for (; b < nBlocks; b += blockDim.x) v[0] += partial[b];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += v[k + 8];
+    const double v0 = v[0] + v[4], v1 = v[1] + v[5], v2 = v[2] + v[6], v3 = v[3] + v[7];
+    const double s = blockSum256((v0 + v1) + (v2 + v3), sh);
+    if (threadIdx.x == 0) {
+        *sumOut = s;
+        total = s;
+    }
+    __syncthreads();
+    const int w = threadIdx.x;
+    if (w < world) {
+        MailSlotDev *slot = (MailSlotDev *)peerMail[w] + parity * 64 + rank;
+        *(volatile double *)&slot->value = total;
+        __threadfence_system();
+        *(volatile unsigned long long *)&slot->seq = seq;
+    }
+}
+
 // ... and, once all `world` contributions of this step have arrived, adds them in rank order -- every rank
 // obtains the same bits -- and forms F_x = 2 (momx - sum / nGlobal) (main_TWOPHASE.cpp:301-308)
 __global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
-                                  double *sumOut, double *forceX)
+                                  double *sumOut, double *forceX, const unsigned long long *flags, unsigned flagMask,
+                                  unsigned long long flagExpect)
 {
     const MailSlotDev *slots = (const MailSlotDev *)mail + parity * 64;
     const int w = threadIdx.x;
     if (w < world) {
         const volatile unsigned long long *f = &slots[w].seq;
         while (*f < seq) __nanosleep(100);
+    } else if (w >= 64 && ((flagMask >> (w - 64)) & 1u)) {
+        // threads 64.. also wait for the arrival counters of the scalar halo (one launch instead of three)
+        const volatile unsigned long long *f = flags + (w - 64);
+        while (*f < flagExpect) __nanosleep(100);
     }
     __threadfence_system();
     __syncthreads();
@@ -133,6 +171,17 @@ __global__ void tilePhiRangesKernel(const int32_t *__restrict__ ptable, int n, i
     }
     __syncthreads();
     if (threadIdx.x == 0) out[blockIdx.x] = make_int4(r[0], r[1], r[2], r[3]);
+}
+
+// waits until every arrival counter selected by `mask` (bit k -> flags[k]) has reached `expect`
+__global__ void waitFlagsKernel(const unsigned long long *flags, unsigned mask, unsigned long long expect)
+{
+    const unsigned k = threadIdx.x;
+    if ((mask >> k) & 1u) {
+        const volatile unsigned long long *f = flags + k;
+        while (*f < expect) __nanosleep(100);
+    }
+    __threadfence_system();
 }
 
 __global__ void fillKernel(double *p, double v, long long count)

@@ -605,7 +605,11 @@ __global__ void waitFlagKernel(const unsigned long long *flag, unsigned long lon
 // one double per rank summed over all ranks through peer memory (kernels.cu)
 __global__ void sumPushKernel(const double *localSum, void *const *peerMail, int rank, int world, int parity, unsigned long long seq);
 __global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
-                                  double *sumOut, double *forceX);
+                                  double *sumOut, double *forceX, const unsigned long long *flags, unsigned flagMask,
+                                  unsigned long long flagExpect);
+__global__ void foldAndPushKernel(const double *__restrict__ partial, int nBlocks, double *sumOut, void *const *peerMail, int rank,
+                                  int world, int parity, unsigned long long seq);
+__global__ void waitFlagsKernel(const unsigned long long *flags, unsigned mask, unsigned long long expect);
 
 // halo pack: buf[k] = X[src[k]] ; unpack: X[dst[k]] = buf[k]   (64-bit slot offsets)
 __global__ void haloPackKernel(double *__restrict__ buf, const double *__restrict__ X,
