@@ -36,7 +36,6 @@ __global__ void haloPushKernel(double *, const double *, const long long *, cons
                                unsigned *, unsigned long long *, unsigned long long);
 __global__ void waitFlagKernel(const unsigned long long *, unsigned long long);
 __global__ void tilePhiRangesKernel(const int32_t *, int, int, int, int, int4 *);
-__global__ void sumPushKernel(const double *, void *const *, int, int, int, unsigned long long);
 __global__ void sumWaitFoldKernel(const void *, int, int, unsigned long long, double, double, double *, double *, const unsigned long long *,
                                   unsigned, unsigned long long);
 __global__ void foldAndPushKernel(const double *, int, double *, void *const *, int, int, int, unsigned long long);
@@ -2051,7 +2050,6 @@ void preloadForPeerStepping(const chimp_lattice *c)
     }
     preloadKernel(haloPushKernel);
     preloadKernel(waitFlagKernel);
-    preloadKernel(sumPushKernel);
     preloadKernel(sumWaitFoldKernel);
     preloadKernel(foldAndPushKernel);
     preloadKernel(waitFlagsKernel);

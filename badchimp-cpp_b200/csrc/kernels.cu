@@ -78,16 +78,6 @@ __global__ void nodeFluxKernel(const int32_t *__restrict__ nodes, int count, con
 // Global sums over peer memory (replaces MPI_Allreduce of one double, main_TWOPHASE.cpp:299): every rank stores its
 // local sum into slot `rank` of every rank's mailbox (value, fence, sequence number) ...
 struct MailSlotDev { double value; unsigned long long seq; };
-__global__ void sumPushKernel(const double *localSum, void *const *peerMail, int rank, int world, int parity, unsigned long long seq)
-{
-    const int w = threadIdx.x;
-    if (w >= world) return;
-    MailSlotDev *slot = (MailSlotDev *)peerMail[w] + parity * 64 + rank;
-    *(volatile double *)&slot->value = *localSum;
-    __threadfence_system();
-    *(volatile unsigned long long *)&slot->seq = seq;
-}
-
 // fold of the per-block partials (fixed order, as fluxForceKernel) and delivery of the local sum in one launch
 __global__ void foldAndPushKernel(const double *__restrict__ partial, int nBlocks, double *sumOut, void *const *peerMail, int rank,
                                   int world, int parity, unsigned long long seq)

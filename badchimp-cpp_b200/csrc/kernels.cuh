@@ -603,7 +603,6 @@ __global__ void haloPushKernel(double *peerX, const double *__restrict__ X, cons
                                unsigned long long value);
 __global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect);
 // one double per rank summed over all ranks through peer memory (kernels.cu)
-__global__ void sumPushKernel(const double *localSum, void *const *peerMail, int rank, int world, int parity, unsigned long long seq);
 __global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
                                   double *sumOut, double *forceX, const unsigned long long *flags, unsigned flagMask,
                                   unsigned long long flagExpect);
