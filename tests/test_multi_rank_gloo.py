@@ -81,3 +81,85 @@ def test_ring_halo_exchange_over_gloo(world, lattice):
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == list(range(world))
     assert all(r[1] for r in res), res
+
+
+def _twophase_worker(rank, world, port, out_q):
+    """scalar (phi) halo of the two-phase slabs over the ring + the balanced cut planes, CPU / gloo"""
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests"))
+    pkg = helpers.load_package()
+    ing = importlib.import_module("badchimp_cpp_b200.ingest")
+    multi = importlib.import_module("badchimp_cpp_b200.multi")
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        G = pkg.geometry
+        nzr = 6
+        shape = (9, 8, nzr * world)
+        geo = G.sphere_pack(shape, 2.5, 0.55, 21).astype(bool)
+        wall = np.where(geo, 0.0, 0.25)
+        # cut planes at equal fluid-node counts: every rank computes the same cuts from its own layer counts
+        layers = torch.from_numpy(geo[:, :, rank * nzr:(rank + 1) * nzr].reshape(-1, nzr).sum(axis=0).astype(np.int64))
+        cuts = multi.balanced_cuts(layers, world)
+        counts = [int(geo[:, :, cuts[k]:cuts[k + 1]].sum()) for k in range(world)]
+        z0, z1 = cuts[rank], cuts[rank + 1]
+        idx = np.arange(z0 - 1, z1 + 1) % shape[2]
+        sl = ing.build_slab_tables(torch.from_numpy(geo[:, :, idx]), "D3Q19", True, torch.from_numpy(wall[:, :, idx]))
+        # phi = a value that identifies the global cell, so that a ghost slot can be checked against its owner
+        gid = np.cumsum(geo.reshape(-1)).reshape(shape).astype(np.float64)
+        own = geo[:, :, z0:z1]
+        lab = sl["labels"][: sl["n"]].numpy()
+        n_extra = sl["n_extra"]
+        phi = np.zeros(sl["n_pad"] + n_extra + 1)
+        phi[: sl["n"]] = gid[:, :, z0:z1][own][lab - 1]
+        phi[sl["n_pad"]: sl["n_pad"] + n_extra] = sl["phi_extra"][:n_extra].numpy()
+        sf = sl["scalar_faces"]
+        ring = multi.RingHalo(rank, world, len(sf["down"][0]), len(sf["down"][1]), len(sf["up"][0]), len(sf["up"][1]), "cpu")
+        ring.send_down[: len(sf["down"][0])] = torch.from_numpy(phi[sf["down"][0].numpy()])
+        ring.send_up[: len(sf["up"][0])] = torch.from_numpy(phi[sf["up"][0].numpy()])
+        ring.exchange()
+        phi[sf["down"][1].numpy()] = ring.recv_down[: len(sf["down"][1])].numpy()
+        phi[sf["up"][1].numpy()] = ring.recv_up[: len(sf["up"][1])].numpy()
+        # every ghost slot now holds the id of the fluid cell of the neighbour's layer it stands for
+        low = gid[:, :, (z0 - 1) % shape[2]][geo[:, :, (z0 - 1) % shape[2]]]
+        up = gid[:, :, z1 % shape[2]][geo[:, :, z1 % shape[2]]]
+        ok = np.array_equal(phi[sf["down"][1].numpy()], low) and np.array_equal(phi[sf["up"][1].numpy()], up)
+        # and the table of a boundary node reaches them: neighbour in +z of a top-layer node is that ghost
+        pt = sl["ptable"].numpy()
+        q_up = [q for q in range(19) if tuple(G.BASIS["D3Q19"][q]) == (0, 0, 1)][0]
+        top = np.argwhere(own[:, :, -1])
+        for slot in range(sl["n"]):
+            cell = np.argwhere(own)[lab[slot] - 1]
+            if cell[2] != z1 - z0 - 1:
+                continue
+            x, y = cell[0], cell[1]
+            want = gid[x, y, z1 % shape[2]] if geo[x, y, z1 % shape[2]] else None
+            got = phi[pt[q_up, slot]]
+            ok = ok and (got == want if want is not None else got in (0.25, 0.0))
+        # the sum of one double over the ranks, added in rank order (what the mailboxes do on the GPUs)
+        mine = torch.tensor([0.1 * (rank + 1)], dtype=torch.float64)
+        gathered = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        total = 0.0
+        for t in gathered:
+            total = total + float(t[0])
+        out_q.put((rank, bool(ok), cuts, counts, total))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_twophase_scalar_ring_and_balanced_cuts_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_twophase_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    assert all(r[2] == res[0][2] and r[4] == res[0][4] for r in res)          # same cuts, same sum bits on every rank
+    cuts, counts = res[0][2], res[0][3]
+    assert cuts[0] == 0 and cuts[-1] == 6 * world and all(b > a for a, b in zip(cuts, cuts[1:]))
+    assert max(counts) - min(counts) <= 2 * 9 * 8                              # within one z-layer of each other
