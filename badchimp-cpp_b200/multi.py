@@ -147,6 +147,26 @@ def attach_ring_twophase_peer(lat, slab, rank, world):
     dist.barrier()
 
 
+def peer_memory_available(local, world, device):
+    """True when every GPU of this node can address every other one (NVLink / NVSwitch, or PCIe peer-to-peer):
+    the peer-memory transport needs it; otherwise callers fall back to the NCCL transport.  The answer is
+    all-reduced so that all ranks take the same branch."""
+    ok = 1.0
+    try:
+        n = torch.cuda.device_count()
+        if n < world:
+            ok = 0.0
+        else:
+            for other in range(world):
+                if other != local and not torch.cuda.can_device_access_peer(local, other):
+                    ok = 0.0
+    except Exception:
+        ok = 0.0
+    t = torch.tensor([ok], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item() == 1.0)
+
+
 def balanced_cuts(my_layer_counts, world):
     """z cut planes such that every rank owns (nearly) the same number of fluid nodes: my_layer_counts holds the
     fluid nodes of each z-layer of this rank's equal-thickness slab (int64 tensor on the rank's device)"""
@@ -186,6 +206,8 @@ def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
     lat = capi.lattice_from_device_table(lattice, slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
                                          slab["labels"].data_ptr(), 1, index_form, local)
     halo_mode = getattr(args, "halo", "peer")
+    if halo_mode == "peer" and not peer_memory_available(local, world, device):
+        halo_mode = "nccl"   # no peer addressing between the GPUs of this node
     if halo_mode == "peer":
         attach_ring_peer(lat, slab, rank, world)
         halo_bytes = 8.0 * (len(slab["faces"]["down"][0]) + len(slab["faces"]["up"][0]))
