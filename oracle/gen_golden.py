@@ -35,7 +35,8 @@ DRIVER = os.path.join(HERE, "_ref", "ref_driver")
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attributes, keep_vtklb=False, checkpoint=False, vtk=False):
+def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attributes, keep_vtklb=False, checkpoint=False, vtk=False,
+                  vtk_ascii=False):
     d = tempfile.mkdtemp(prefix="golden_")
     os.makedirs(os.path.join(d, "out"))
     basis = lattice if lattice != "D3Q27" else G.BASIS["D3Q27"].astype(int)
@@ -51,7 +52,7 @@ def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attribu
     if vtk:  # the reference's own Output<LT>::write (io/Output.h, io/VTK.h) after the last step
         vdir = os.path.join(OUT, name + ".vtk")
         shutil.rmtree(vdir, ignore_errors=True)
-        cmd += ["--vtk", vdir + "/"]
+        cmd += ["--vtk", vdir + "/"] + (["--vtk-ascii"] if vtk_ascii else [])
     subprocess.run(cmd, check=True, capture_output=True)
     gold = {"geo": np.asarray(geo, dtype=np.int32), "lattice": lattice, "periodic": periodic, "case": case,
             "steps": steps, "dump": np.array(dump), "args": np.array([str(a) for a in args]), "nranks": nranks}
@@ -118,6 +119,10 @@ def vtk_goldens():
     pack = G.sphere_pack(shape, 1.8, 0.7, 3).astype(int)
     run_reference("vtk_std_d3q19_p2", G.z_slab_rank_map(pack, 2), "D3Q19", "xyz", "std_case", 3, [3],
                   ["--tau", 0.8, "--force", "1e-5,2e-6,-3e-6"], {"init_rho": np.ones(shape)}, vtk=True)
+    chan = np.ones((5, 6), dtype=int)
+    chan[:, 0] = chan[:, -1] = 0
+    run_reference("vtk_ascii_d2q9_p1", chan, "D2Q9", "x", "std_case", 2, [2], ["--tau", 0.8, "--force", "1e-5,0,0"],
+                  {"init_rho": np.ones(chan.shape)}, vtk=True, vtk_ascii=True)
     pack2d = G.sphere_pack((9, 8), 2.0, 0.7, 9).astype(int)
     x2 = np.arange(9)[:, None] * np.ones((9, 8))
     r2 = (x2 < 4).astype(float)

@@ -64,6 +64,7 @@ struct Opts {
     std::set<int> dumpSteps;
     bool dumpTables = true, dumpF = true, timing = false;
     std::string vtk;        // directory for the reference's own Output<LT>::write() after the last step
+    bool vtkAscii = false;  // ... through Output<LT, double, VTK::ASCII>
     std::string checkpoint; // prefix for the reference's own writeToFile() dumps after the last step
     double tau = 0.8, tauSym = 0.0, tauAnti = 0.0; // TRT when tauSym > 0
     std::vector<double> force{0, 0, 0};
@@ -261,11 +262,19 @@ double runStdCase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid,
         int nProcs = 1;
         MPI_Comm_size(MPI_COMM_WORLD, &nProcs);
         std::vector<int> bulkNodes = bulk;
-        Output<LT> output(grid, bulkNodes, o.vtk, vtklb.getRank(), nProcs);
-        output.add_file("lb_run");
-        output.add_scalar_variables({"rho"}, {rho});
-        output.add_vector_variables({"vel"}, {vel});
-        output.write(o.steps);
+        if (o.vtkAscii) {
+            Output<LT, double, VTK::ASCII> output(grid, bulkNodes, o.vtk, vtklb.getRank(), nProcs);
+            output.add_file("lb_run");
+            output.add_scalar_variables({"rho"}, {rho});
+            output.add_vector_variables({"vel"}, {vel});
+            output.write(o.steps);
+        } else {
+            Output<LT> output(grid, bulkNodes, o.vtk, vtklb.getRank(), nProcs);
+            output.add_file("lb_run");
+            output.add_scalar_variables({"rho"}, {rho});
+            output.add_vector_variables({"vel"}, {vel});
+            output.write(o.steps);
+        }
     }
     return secs;
 }
@@ -620,6 +629,7 @@ int main(int argc, char **argv)
         else if (a == "--time") o.timing = true;
         else if (a == "--checkpoint") o.checkpoint = next();
         else if (a == "--vtk") o.vtk = next();
+        else if (a == "--vtk-ascii") o.vtkAscii = true;
         else if (a == "--tau") o.tau = std::stod(next());
         else if (a == "--trt") { auto v = parseList(next()); o.tauSym = v[0]; o.tauAnti = v[1]; }
         else if (a == "--force") { auto v = parseList(next()); v.resize(3, 0.0); o.force = v; }
