@@ -51,7 +51,7 @@ SYMBOLS = [
     "chimp_num_neighbors", "chimp_neighbor_info", "chimp_send_buffer_dev", "chimp_recv_buffer_dev",
     "chimp_set_exchange_callback", "chimp_set_stream", "chimp_synchronize", "chimp_num_own_nodes",
     "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_irregular_fraction",
-    "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_init_uniform",
+    "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_step_twophase_timed", "chimp_peer_mode", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
     "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_capillary_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles_twophase", "chimp_local_pointers_twophase", "chimp_connect_peer_scalar", "chimp_connect_world", "chimp_host_scalar_halo_lists", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
@@ -255,6 +255,21 @@ class Lattice:
         p.n_fluid_global = int(n_fluid_global)
         _check(lib().chimp_step_twophase(self.h, C.byref(p), C.c_int(n_steps)))
 
+    def _twophase_params(self, tau0, tau1, sigma, beta, momx, force, n_fluid_global):
+        p = TwoPhaseParams()
+        p.tau0, p.tau1, p.sigma, p.beta, p.momx = tau0, tau1, sigma, beta, momx
+        F = list(force) + [0.0] * (3 - len(force))
+        p.force[0], p.force[1], p.force[2] = F[0], F[1], F[2]
+        p.n_fluid_global = int(n_fluid_global)
+        return p
+
+    def step_twophase_timed(self, n_steps, tau0, tau1, sigma, beta, momx, force, n_fluid_global):
+        """runs n_steps and returns their device time in ms (CUDA events on the engine's own stream)"""
+        p = self._twophase_params(tau0, tau1, sigma, beta, momx, force, n_fluid_global)
+        ms = C.c_double()
+        _check(lib().chimp_step_twophase_timed(self.h, C.byref(p), C.c_int(n_steps), C.byref(ms)))
+        return ms.value
+
     def _single_params(self, tau, force, trt):
         p = SingleParams()
         p.collision = TRT if trt else BGK
@@ -366,6 +381,12 @@ class Lattice:
         hb = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles)) if handles is not None else None
         pp = (C.c_void_p * world)(*pointers) if pointers is not None else None
         _check(lib().chimp_connect_world(self.h, C.c_int(rank), C.c_int(world), hb, C.c_int(1 if pointers is not None else 0), pp))
+
+    def peer_mode(self):
+        """(mode, why): 0 no peer halos, 1 separate push launches, 2 fused into the step kernel"""
+        buf = C.create_string_buffer(256)
+        mode = int(lib().chimp_peer_mode(self.h, buf, C.c_int(256)))
+        return mode, buf.value.decode()
 
     def plane_stride(self):
         return int(lib().chimp_plane_stride(self.h))
@@ -491,7 +512,7 @@ def lattice_from_device_table(lattice: str, n_bulk, n_pad, n_halo, table_ptr, la
     obj.lattice = lattice
     obj.nq = len(G.BASIS[lattice])
     obj.nd = G.BASIS[lattice].shape[1]
-    obj.n_nodes = 0
+    obj.n_nodes = n_bulk + 1   # labels 1..N are the leading rows of a reference-layout field (row 0 = dummy node)
     obj.n_fields = n_fields
     obj._cb = None
     obj.h = C.c_void_p()

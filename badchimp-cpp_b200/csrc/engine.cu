@@ -26,20 +26,8 @@
 #include "twophase_fused.cuh"
 
 namespace chimp {
-__global__ void fluxForceKernel(const double *, int, double, double, double *, double *, int);
-__global__ void massFinalizeKernel(const double *, int, const double *, double *, double *);
 __global__ void fillKernel(double *p, double v, long long count);
-__global__ void invertLabelsKernel(const int32_t *, int, int32_t *);
-__global__ void foldRowsKernel(const double *, int, double *);
-__global__ void nodeFluxKernel(const int32_t *, int, const int32_t *, int, const double *, const double *, double *);
-__global__ void haloPushKernel(double *, const double *, const long long *, const long long *, int, int, long long, long long,
-                               unsigned *, unsigned long long *, unsigned long long);
-__global__ void waitFlagKernel(const unsigned long long *, unsigned long long);
 __global__ void tilePhiRangesKernel(const int32_t *, int, int, int, int, int4 *);
-__global__ void sumWaitFoldKernel(const void *, int, int, unsigned long long, double, double, double *, double *, const unsigned long long *,
-                                  unsigned, unsigned long long);
-__global__ void foldAndPushKernel(const double *, int, double *, void *const *, int, int, int, unsigned long long);
-__global__ void waitFlagsKernel(const unsigned long long *, unsigned, unsigned long long);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *, int, long long);
 __global__ void kernelTableKernel(const int32_t *, int32_t *, int, int, int, int, long long);
@@ -54,6 +42,9 @@ std::map<std::string, void *> g_ipcOpen; // CUDA IPC mappings of this process (k
 int openIpc(const unsigned char *handle64, void **out);
 int labelRangeOf(chimp_lattice *c);
 void preloadForPeerStepping(const chimp_lattice *c);
+int buildPeerTables(chimp_lattice *c);
+int checkDeviceError(chimp_lattice *c);
+void awaitPeers(chimp_lattice *c);
 std::atomic<long long> g_launches{0};
 
 int fail(const char *fmt, ...)
@@ -96,6 +87,7 @@ struct Neighbor {
     std::vector<int32_t> sendNodes, nDirSend, dirSend, recvNodes, nDirRecv, dirRecv;
     long long sendCount = 0, recvCount = 0; // per field
     long long *d_sendSrc = nullptr, *d_recvDst = nullptr;
+    std::vector<long long> hSrc, hPeerDst; // host copies: send list and the peer slots it lands in (fused peer tables)
     long long *d_phiSendSrc = nullptr, *d_phiRecvDst = nullptr; // scalar (phi) halo: slots of the phi array
     double *d_phiSendBuf = nullptr, *d_phiRecvBuf = nullptr;
     long long phiSendCount = 0, phiRecvCount = 0;
@@ -179,6 +171,20 @@ struct chimp_lattice {
     void *exchangeUser = nullptr, *scalarExchangeUser = nullptr;
     unsigned long long *d_flags = nullptr; // arrival counters written by the neighbours, one per face (max 8)
     bool peerHalos = false;
+    // peer exchange fused into the step kernel (PeerView): per halo-coupled node the directions that leave the rank
+    // and where they land; built once every face is connected
+    bool peerFused = false;
+    uint32_t *d_sendMask = nullptr, *d_sendMask2 = nullptr;
+    int32_t *d_sendDst = nullptr, *d_sendDst2 = nullptr;
+    int peerPad = 0, peerBlocks = 0;
+    unsigned *d_peerCounter = nullptr;
+    unsigned *h_error = nullptr, *d_error = nullptr; // host-mapped error word raised by a device-side arrival timeout
+    unsigned long long timeoutNs = 20000000000ull;
+    unsigned long long *d_trace = nullptr;           // CHIMP_TRACE: per-step device timestamps [traceCap][4]
+    unsigned long long *traceCursor = nullptr;
+    int traceCap = 0;
+    bool trace = false, tpFusedEnv = false, peerFusedEnv = true;
+    std::string peerWhy;
     // two-phase over peer memory: sum mailbox of every rank (world pointers on the device), my rank / world size
     MailSlot *d_mail = nullptr;
     MailSlot **d_peerMail = nullptr;
@@ -224,7 +230,40 @@ int allocateState(chimp_lattice *c)
     // arrival counters written by the neighbours: [0, 8) population faces, [8, 16) scalar (phi) faces
     CUDA_OK(cudaMalloc(&c->d_flags, 16 * sizeof(unsigned long long)));
     CUDA_OK(cudaMemsetAsync(c->d_flags, 0, 16 * sizeof(unsigned long long), c->stream));
+    // error word raised by device-side waits that time out (a peer that never arrives): host-mapped, so it can be
+    // read even while a kernel is still running
+    CUDA_OK(cudaHostAlloc((void **)&c->h_error, sizeof(unsigned), cudaHostAllocMapped));
+    *c->h_error = 0u;
+    CUDA_OK(cudaHostGetDevicePointer((void **)&c->d_error, c->h_error, 0));
+    // environment switches are read once, here
+    auto envInt = [](const char *name, long long dflt) {
+        const char *v = getenv(name);
+        return v ? atoll(v) : dflt;
+    };
+    c->trace = envInt("CHIMP_TRACE", 0) == 1;
+    c->tpFusedEnv = envInt("CHIMP_TP_FUSED", 0) == 1;
+    c->peerFusedEnv = envInt("CHIMP_PEER_FUSED", 1) != 0;
+    c->timeoutNs = (unsigned long long)std::max(1ll, envInt("CHIMP_PEER_TIMEOUT_MS", 20000)) * 1000000ull;
     return 0;
+}
+
+// a device-side wait gave up (CHIMP_PEER_TIMEOUT_MS): the state is no longer meaningful
+int checkDeviceError(chimp_lattice *c)
+{
+    if (!c->h_error || *c->h_error == 0u) return 0;
+    const unsigned code = *c->h_error;
+    return fail("rank %d: a neighbour rank did not arrive within %.1f s (%s); all ranks must step the same number of times",
+                c->worldRank, c->timeoutNs * 1e-9,
+                code == 1u ? "population halo counter" : code == 2u ? "global-sum mailbox" : "scalar halo counter");
+}
+
+// peer halos: everything that reads or overwrites halo-in slots outside the step kernels (transfers, reductions, the
+// mass-change pass) first waits, on the engine's stream, until every neighbour's stores of the last step have landed
+void awaitPeers(chimp_lattice *c)
+{
+    if (!c->peerHalos || c->nbrs.empty() || c->steps == 0) return;
+    waitFlagsKernel<<<1, 32, 0, c->stream>>>(c->d_flags, (1u << c->nbrs.size()) - 1u, (unsigned long long)c->steps, c->timeoutNs, c->d_error);
+    ++g_launches;
 }
 
 int buildKernelTable(chimp_lattice *c)
@@ -297,7 +336,11 @@ void launchSingle(const StepArgs &a, bool mom, cudaStream_t s)
     if (count <= 0) return;
     const int block = CHIMP_BLOCK;
     const unsigned grid = (unsigned)((count + block - 1) / block);
-    if (mom) collideStreamKernel<L, COLL, ONEPHASE, true, IDX><<<grid, block, 0, s>>>(a);
+    if (IDX == IDX_COMPACT && a.peer.blocks > 0) {
+        // halo-coupled blocks first, their remote stores and arrival counters inside the launch
+        if (mom) collideStreamKernel<L, COLL, ONEPHASE, true, IDX_COMPACT, true><<<grid, block, 0, s>>>(a);
+        else collideStreamKernel<L, COLL, ONEPHASE, false, IDX_COMPACT, true><<<grid, block, 0, s>>>(a);
+    } else if (mom) collideStreamKernel<L, COLL, ONEPHASE, true, IDX><<<grid, block, 0, s>>>(a);
     else collideStreamKernel<L, COLL, ONEPHASE, false, IDX><<<grid, block, 0, s>>>(a);
     ++g_launches;
 }
@@ -426,11 +469,15 @@ int chimp_add_halfway_bb(chimp_lattice *c, int n_bnd, const int32_t *nodes, cons
 {
     if (check(c, false)) return 1;
     const int nQ = c->li.nQ, P = c->li.nPairs;
+    if (n_bnd < 0 || (n_bnd > 0 && (!nodes || !n_beta || !n_gamma || !n_delta || !links))) return fail("bad bounce-back arguments");
     for (int b = 0; b < n_bnd; ++b) {
         const int node = nodes[b];
         if (node <= 0 || node >= c->nNodes) return fail("bounce-back node %d out of range", node);
+        if (n_beta[b] < 0 || n_gamma[b] < 0 || n_delta[b] < 0) return fail("bounce-back node %d: negative link count", node);
         if (n_beta[b] + n_gamma[b] + n_delta[b] != P) return fail("bounce-back node %d: link counts do not sum to nDirPairs", node);
         const int32_t *l = links + (size_t)b * P;
+        for (int k = 0; k < P; ++k)
+            if (l[k] < 0 || l[k] >= nQ - 1) return fail("bounce-back node %d: link direction %d outside [0,%d)", node, l[k], nQ - 1);
         // LBhalfwaybb.h:52-61
         for (int k = 0; k < n_beta[b]; ++k) {
             const int beta = l[k], br = revDir(c->li, beta);
@@ -465,6 +512,13 @@ int chimp_add_neighbor(chimp_lattice *c, int neig_rank, int n_send, const int32_
 {
     if (check(c, false)) return 1;
     if (!c->nbrs.empty() && c->nbrs.back().rank >= neig_rank) return fail("neighbour ranks must be added in ascending order");
+    if (n_send < 0 || n_recv < 0 || (n_send > 0 && (!nodes_to_send || !n_dir_send || !dir_list_send)) ||
+        (n_recv > 0 && (!nodes_received || !n_dir_recv || !dir_list_recv)))
+        return fail("bad exchange lists for neighbour %d", neig_rank);
+    for (int k = 0; k < n_send; ++k)
+        if (n_dir_send[k] < 0) return fail("neighbour %d: negative direction count", neig_rank);
+    for (int k = 0; k < n_recv; ++k)
+        if (n_dir_recv[k] < 0) return fail("neighbour %d: negative direction count", neig_rank);
     Neighbor nb;
     nb.rank = neig_rank;
     nb.sendNodes.assign(nodes_to_send, nodes_to_send + n_send);
@@ -486,6 +540,7 @@ int chimp_add_neighbor(chimp_lattice *c, int neig_rank, int n_send, const int32_
 int chimp_set_solid_boundary(chimp_lattice *c, int n_solid, const int32_t *solid_nodes)
 {
     if (check(c, false)) return 1;
+    if (n_solid < 0 || (n_solid > 0 && !solid_nodes)) return fail("bad solid boundary list");
     c->solidBnd.assign(solid_nodes, solid_nodes + n_solid);
     return 0;
 }
@@ -725,6 +780,7 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
     for (size_t k = 0; k < c->nbrs.size(); ++k) {
         Neighbor &nb = c->nbrs[k];
         const std::vector<long long> &src = c->hSendSrc[k], &dst = c->hRecvDst[k];
+        nb.hSrc = src;
         if (!src.empty()) {
             CUDA_OK(cudaMalloc(&nb.d_sendSrc, src.size() * sizeof(long long)));
             CUDA_OK(cudaMemcpy(nb.d_sendSrc, src.data(), src.size() * sizeof(long long), cudaMemcpyHostToDevice));
@@ -829,6 +885,9 @@ void chimp_destroy(chimp_lattice *c)
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
     freeDev(c->d_rho); freeDev(c->d_vel); freeDev(c->d_flags); freeDev(c->d_slotOf);
     freeDev(c->d_mail); freeDev(c->d_peerMail);
+    freeDev(c->d_sendMask); freeDev(c->d_sendDst); freeDev(c->d_sendMask2); freeDev(c->d_sendDst2);
+    freeDev(c->d_peerCounter); freeDev(c->d_trace);
+    if (c->h_error) cudaFreeHost(c->h_error);
     freeDev(c->d_tpSeq); freeDev(c->d_tpDeps); freeDev(c->d_tpDone); freeDev(c->d_tpTicket); freeDev(c->d_tpMom);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
@@ -906,6 +965,7 @@ int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
     Staging st;
     if (acquireStaging(c, bytes, st)) return 1;
     double *d_aos = st.ptr;
+    awaitPeers(c); // a neighbour's stores of the last step must not land on top of the uploaded halo-in slots
     CUDA_OK(cudaMemcpyAsync(d_aos, f_aos + (size_t)c->labelMin * rowDoubles, bytes, cudaMemcpyHostToDevice, c->stream));
     const unsigned grid = (unsigned)((c->n + 255) / 256);
     double *X = c->d_f[c->cur];
@@ -918,7 +978,7 @@ int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
     ++g_launches;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return checkDeviceError(c);
 }
 
 int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
@@ -935,6 +995,7 @@ int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
     if (acquireStaging(c, bytes, st)) return 1;
     double *d_aos = st.ptr;
     if (!c->labelsContiguous) CUDA_OK(cudaMemcpyAsync(d_aos, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    awaitPeers(c); // the gather reads the halo-in slots the neighbours filled during the last step
     const unsigned grid = (unsigned)((c->n + 255) / 256);
     const double *X = c->d_f[c->cur];
     double *shifted = d_aos - (size_t)c->labelMin * rowDoubles;
@@ -947,7 +1008,7 @@ int chimp_download_lbfield(chimp_lattice *c, double *f_aos)
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(host, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return checkDeviceError(c);
 }
 
 static int downloadPlanes(chimp_lattice *c, double *host, const double *planes, int nComp, int aosStride, int aosOffset)
@@ -969,7 +1030,7 @@ static int downloadPlanes(chimp_lattice *c, double *host, const double *planes, 
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(hostRows, d_aos, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return checkDeviceError(c);
 }
 
 int chimp_download_rho(chimp_lattice *c, double *rho_sca, int n_fields_host)
@@ -1113,8 +1174,41 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom, bool cal
     if (fillStepArgs(c, p, a)) return 1;
     fillPlanes(c, a.pl);
     double *const foutBuf = c->d_f[c->cur ^ 1];
-    if (c->onePhase && c->nLabels > 1 && massChangePass(c, a)) return 1;
+    if (c->onePhase && c->nLabels > 1) {
+        awaitPeers(c); // the pass gathers through the halo-in slots
+        if (massChangePass(c, a)) return 1;
+    }
     if (c->nbrs.empty()) {
+        a.begin = 0;
+        a.end = c->n;
+        dispatchSingleLattice(c, a, p->collision, mom, c->stream);
+        return 0;
+    }
+    if (c->peerHalos && c->peerFused) {
+        // one launch per step: the halo-coupled nodes occupy the first blocks; those blocks wait for the neighbours'
+        // arrival counters, store the outgoing populations into the neighbours' halo-in slots and publish this step
+        PeerView &pv = a.peer;
+        pv.blocks = c->peerBlocks;
+        pv.nFaces = (int)c->nbrs.size();
+        pv.pad = c->peerPad;
+        pv.mask = c->d_sendMask;
+        pv.dst = c->d_sendDst;
+        pv.mask2 = c->d_sendMask2;
+        pv.dst2 = c->d_sendDst2;
+        const int outIdx = c->cur ^ 1;
+        for (int k = 0; k < pv.nFaces; ++k) {
+            const Neighbor &nb = c->nbrs[k];
+            pv.out[k] = nb.peerX[outIdx];
+            pv.stride[k] = nb.peerFieldStride / c->li.nQ;
+            pv.flagOut[k] = nb.peerFlags + nb.peerFace;
+        }
+        pv.flagIn = c->d_flags;
+        pv.expect = (unsigned long long)c->steps;
+        pv.publish = (unsigned long long)c->steps + 1;
+        pv.counter = c->d_peerCounter;
+        pv.error = c->d_error;
+        pv.timeoutNs = c->timeoutNs;
+        pv.trace = c->traceCursor;
         a.begin = 0;
         a.end = c->n;
         dispatchSingleLattice(c, a, p->collision, mom, c->stream);
@@ -1128,10 +1222,8 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom, bool cal
     if (c->peerHalos) {
         // the halo-in slots of the buffer read now were stored by the neighbours during their previous
         // step: wait until every face has reported that step (the flag counts completed pushes)
-        for (size_t k = 0; k < c->nbrs.size(); ++k) {
-            waitFlagKernel<<<1, 1, 0, c->haloStream>>>(c->d_flags + k, (unsigned long long)c->steps);
-            ++g_launches;
-        }
+        waitFlagsKernel<<<1, 32, 0, c->haloStream>>>(c->d_flags, (1u << c->nbrs.size()) - 1u, (unsigned long long)c->steps, c->timeoutNs, c->d_error);
+        ++g_launches;
     }
     a.begin = 0;
     a.end = c->nBoundary ? c->nBoundary : c->n;
@@ -1168,7 +1260,7 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom, bool cal
 int stepEnd(chimp_lattice *c)
 {
     double *fout = c->d_f[c->cur ^ 1];
-    if (!c->nbrs.empty()) {
+    if (!c->nbrs.empty() && !(c->peerHalos && c->peerFused)) {
         if (!c->peerHalos) unpackHalos(c, fout);
         CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
@@ -1202,11 +1294,44 @@ int chimp_step_single(chimp_lattice *c, const chimp_single_params *p, int n_step
 {
     if (check(c, true)) return 1;
     CUDA_OK(cudaSetDevice(c->device));
+    // CHIMP_TRACE=1 with the fused peer step: device timestamps per step (first block start, arrival counters
+    // published, longest counter wait, last block end), printed per rank as averages over the call
+    const bool trace = c->trace && c->peerHalos && c->peerFused && n_steps > 0;
+    if (trace) {
+        if (c->traceCap < n_steps) {
+            freeDev(c->d_trace);
+            CUDA_OK(cudaMalloc(&c->d_trace, (size_t)n_steps * 4 * sizeof(unsigned long long)));
+            c->traceCap = n_steps;
+        }
+        CUDA_OK(cudaMemsetAsync(c->d_trace, 0, (size_t)n_steps * 4 * sizeof(unsigned long long), c->stream));
+    }
     for (int s = 0; s < n_steps; ++s) {
+        c->traceCursor = trace ? c->d_trace + 4 * (size_t)s : nullptr;
         if (stepBegin(c, p, s == n_steps - 1, true)) return 1;
         if (stepEnd(c)) return 1;
     }
+    c->traceCursor = nullptr;
     CUDA_OK(cudaGetLastError());
+    if (trace) {
+        std::vector<unsigned long long> t((size_t)n_steps * 4);
+        CUDA_OK(cudaMemcpyAsync(t.data(), c->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        double pub = 0, run = 0, wait = 0, gap = 0, waitMax = 0;
+        for (int s = 0; s < n_steps; ++s) {
+            const unsigned long long *e = &t[4 * (size_t)s];
+            pub += (double)(e[1] - e[0]);
+            run += (double)(e[3] - e[0]);
+            wait += (double)e[2];
+            waitMax = std::max(waitMax, (double)e[2]);
+            if (s) gap += (double)((long long)e[0] - (long long)t[4 * (size_t)(s - 1) + 3]);
+        }
+        const double k = 1e-6 / n_steps;
+        fprintf(stderr,
+                "[chimp trace] rank %d: %d steps, %d own nodes (%d halo-coupled blocks of %d); ms/step: kernel %.4f | start -> halo published %.4f | "
+                "longest counter wait %.4f (max %.4f) | gap between launches %.4f\n",
+                c->worldRank, n_steps, c->n, c->peerBlocks, (c->n + CHIMP_BLOCK - 1) / CHIMP_BLOCK, run * k, pub * k, wait * k, waitMax * 1e-6,
+                n_steps > 1 ? gap * 1e-6 / (n_steps - 1) : 0.0);
+    }
     return 0;
 }
 
@@ -1299,6 +1424,7 @@ int chimp_download_moments_device_order(chimp_lattice *c, double *rho, double *v
     if (check(c, true)) return 1;
     CUDA_OK(cudaSetDevice(c->device));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (checkDeviceError(c)) return 1;
     if (rho) CUDA_OK(cudaMemcpy(rho, c->d_rho, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost));
     if (vel)
         for (int d = 0; d < c->li.nD; ++d)
@@ -1527,7 +1653,7 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     a.forceX = c->d_forceX;
     // opt-in (CHIMP_TP_FUSED=1): the fused launch moves 15 % fewer DRAM bytes but is latency-bound at 4 blocks/SM and
     // measured slower than the two kernels below on B200 (profiles/r01_twophase_fused_experiment.txt)
-    const bool fused = !multi && c->lattice != CHIMP_D3Q27 && getenv("CHIMP_TP_FUSED") && atoi(getenv("CHIMP_TP_FUSED")) == 1;
+    const bool fused = !multi && c->lattice != CHIMP_D3Q27 && c->tpFusedEnv;
     if (fused) return stepTwoPhaseFused(c, p, a, n_steps);
     c->forceLast = 0;
     c->tpMomValid = false;
@@ -1535,7 +1661,7 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     const unsigned gridAll = (unsigned)((c->n + 255) / 256);
     // CHIMP_TRACE=1: phase durations on the main stream (moment pass / exchange + global sum / boundary collide /
     // interior collide + halo completion), averaged over the call and printed per rank
-    const bool trace = getenv("CHIMP_TRACE") && atoi(getenv("CHIMP_TRACE")) == 1;
+    const bool trace = c->trace;
     std::vector<cudaEvent_t> ev;
     auto mark = [&]() {
         if (!trace) return;
@@ -1551,7 +1677,7 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
         mark();
         if (multi && c->peerTwoPhase) {
             // the halo-in slots read by the moment pass were stored by the neighbours during their previous step
-            waitFlagsKernel<<<1, 32, 0, c->stream>>>(c->d_flags, (1u << c->nbrs.size()) - 1u, (unsigned long long)c->steps);
+            waitFlagsKernel<<<1, 32, 0, c->stream>>>(c->d_flags, (1u << c->nbrs.size()) - 1u, (unsigned long long)c->steps, c->timeoutNs, c->d_error);
             ++g_launches;
         }
         mark();
@@ -1583,7 +1709,7 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
             for (size_t k = 0; k < c->nbrs.size(); ++k)
                 if (c->nbrs[k].phiRecvCount) phiMask |= 1u << k;
             sumWaitFoldKernel<<<1, kMaxWorld + 32, 0, c->stream>>>(c->d_mail, c->worldSize, parity, seq, p->momx, (double)p->n_fluid_global,
-                                                                  c->d_fluxSum, c->d_forceX, c->d_flags + 8, phiMask, seq);
+                                                                  c->d_fluxSum, c->d_forceX, c->d_flags + 8, phiMask, seq, c->timeoutNs, c->d_error);
             ++g_launches;
         } else if (multi) {
             // communciateScalarField(cgField) (:287) and MPI_Allreduce of the momentum sum (:299)
@@ -1674,6 +1800,25 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     return 0;
 }
 
+int chimp_step_twophase_timed(chimp_lattice *c, const chimp_twophase_params *p, int n_steps, double *ms)
+{
+    if (check(c, true)) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, c->stream));
+    const int rc = chimp_step_twophase(c, p, n_steps);
+    CUDA_OK(cudaEventRecord(e1, c->stream));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float t = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = t;
+    return rc;
+}
+
 int chimp_download_phase_field(chimp_lattice *c, double *cg)
 {
     if (check(c, true)) return 1;
@@ -1728,6 +1873,7 @@ int chimp_flux_force(chimp_lattice *c, int field_no, int cart_dir, double fixed_
     fillIndexView(c, a.idx);
     fillPlanes(c, a.pl);
     const long long fieldOff = (long long)field_no * c->li.nQ * c->stride;
+    awaitPeers(c);
     switch (c->lattice) {
     case CHIMP_D2Q9: launchMomentumSum<D2Q9>(c, a, fieldOff, cart_dir, grid); break;
     case CHIMP_D3Q19: launchMomentumSum<D3Q19>(c, a, fieldOff, cart_dir, grid); break;
@@ -1744,7 +1890,7 @@ int chimp_flux_force(chimp_lattice *c, int field_no, int cart_dir, double fixed_
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(force_out, c->d_forceX + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return checkDeviceError(c);
 }
 
 extern "C++" {
@@ -1778,6 +1924,7 @@ int chimp_capillary_force(chimp_lattice *c, int cart_dir, double sigma_cap_numb,
     a.nPad = c->nPad;
     fillIndexView(c, a.idx);
     fillPlanes(c, a.pl);
+    awaitPeers(c);
     switch (c->lattice) {
     case CHIMP_D2Q9: launchCapNumberSums<D2Q9>(c, a, cart_dir, grid, d_partial); break;
     case CHIMP_D3Q19: launchCapNumberSums<D3Q19>(c, a, cart_dir, grid, d_partial); break;
@@ -1877,6 +2024,7 @@ int chimp_add_halo_face(chimp_lattice *c, int neig_rank, long long n_send, const
     nb.rank = neig_rank;
     nb.sendCount = n_send;
     nb.recvCount = n_recv;
+    nb.hSrc.assign(send_src, send_src + n_send);
     if (n_send) {
         CUDA_OK(cudaMalloc(&nb.d_sendSrc, (size_t)n_send * sizeof(long long)));
         CUDA_OK(cudaMemcpy(nb.d_sendSrc, send_src, (size_t)n_send * sizeof(long long), cudaMemcpyHostToDevice));
@@ -1966,6 +2114,7 @@ int chimp_connect_peer(chimp_lattice *c, int k, const unsigned char *peer_handle
     nb.peerFieldStride = peer_field_stride;
     nb.peerFace = peer_face;
     freeDev(nb.d_peerDst);
+    nb.hPeerDst.assign(peer_dst, peer_dst + n_dst);
     if (n_dst) {
         CUDA_OK(cudaMalloc(&nb.d_peerDst, (size_t)n_dst * sizeof(long long)));
         CUDA_OK(cudaMemcpy(nb.d_peerDst, peer_dst, (size_t)n_dst * sizeof(long long), cudaMemcpyHostToDevice));
@@ -1977,12 +2126,79 @@ int chimp_connect_peer(chimp_lattice *c, int k, const unsigned char *peer_handle
     bool all = true;
     for (auto &x : c->nbrs) all = all && x.peerFlags != nullptr;
     c->peerHalos = all;
-    if (all) preloadForPeerStepping(c);
+    if (all) {
+        if (buildPeerTables(c)) return 1;
+        preloadForPeerStepping(c);
+    }
     return 0;
 }
 
 extern "C++" {
 namespace {
+// Tables of the fused peer exchange (PeerView): for every halo-coupled node the directions whose written population
+// also goes to a neighbour rank, and the slot of the neighbour's plane it lands in.  The fused form needs the
+// halo-coupled nodes in the leading slots (boundary_first), every outgoing population in the plane of its own
+// direction on the other side (true for MonLatMpi lists and the structured ingest) and the compact index; otherwise
+// the step keeps the separate haloPushKernel launches.
+int buildPeerTables(chimp_lattice *c)
+{
+    c->peerFused = false;
+    freeDev(c->d_sendMask); freeDev(c->d_sendDst); freeDev(c->d_sendMask2); freeDev(c->d_sendDst2);
+    c->peerWhy = "";
+    auto notFused = [&](const char *why) { c->peerWhy = why; return 0; };
+    if (!c->peerFusedEnv) return notFused("switched off (CHIMP_PEER_FUSED=0)");
+    if (c->nFields != 1) return notFused("two-field lattice");
+    if (c->indexForm != CHIMP_INDEX_COMPACT) return notFused("table index form");
+    if (c->nBoundary <= 0) return notFused("halo-coupled nodes are not in the leading slots (boundary_first)");
+    if (c->nbrs.size() > (size_t)kMaxFaces) return notFused("more than 8 faces");
+    const int nQ = c->li.nQ;
+    const int blocks = (c->nBoundary + CHIMP_BLOCK - 1) / CHIMP_BLOCK;
+    const int pad = blocks * CHIMP_BLOCK;
+    std::vector<uint32_t> mask(pad, 0u), mask2;
+    std::vector<int32_t> dst((size_t)nQ * pad, -1), dst2;
+    for (size_t k = 0; k < c->nbrs.size(); ++k) {
+        const Neighbor &nb = c->nbrs[k];
+        if ((long long)nb.hSrc.size() != nb.sendCount || (long long)nb.hPeerDst.size() != nb.sendCount) return notFused("send list not available on the host");
+        if (nb.peerFieldStride % nQ) return notFused("peer field stride is not a multiple of nQ");
+        const long long peerPlane = nb.peerFieldStride / nQ;
+        for (long long e = 0; e < nb.sendCount; ++e) {
+            const long long q = nb.hSrc[e] / c->stride, slot = nb.hSrc[e] % c->stride;
+            const long long dq = nb.hPeerDst[e] / peerPlane, dslot = nb.hPeerDst[e] % peerPlane;
+            if (slot >= c->nBoundary) return notFused("a sent population belongs to a node outside the leading halo-coupled slots");
+            if (dq != q) return notFused("a sent population changes its direction plane on the other side");
+            if (dslot >= (1ll << 28)) return notFused("peer plane too long for the packed destination word");
+            const int32_t word = (int32_t)((k << 28) | dslot);
+            if ((mask[slot] >> q) & 1u) {
+                // the reference's lists name a node once per ghost image the receiver holds of it: second destination
+                if (mask2.empty()) { mask2.assign(pad, 0u); dst2.assign((size_t)nQ * pad, -1); }
+                if ((mask2[slot] >> q) & 1u) return notFused("a population is sent to more than two places");
+                mask2[slot] |= 1u << q;
+                dst2[(size_t)q * pad + slot] = word;
+                continue;
+            }
+            mask[slot] |= 1u << q;
+            dst[(size_t)q * pad + slot] = word;
+        }
+    }
+    CUDA_OK(cudaMalloc(&c->d_sendMask, mask.size() * sizeof(uint32_t)));
+    CUDA_OK(cudaMemcpy(c->d_sendMask, mask.data(), mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->d_sendDst, dst.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMemcpy(c->d_sendDst, dst.data(), dst.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!mask2.empty()) {
+        CUDA_OK(cudaMalloc(&c->d_sendMask2, mask2.size() * sizeof(uint32_t)));
+        CUDA_OK(cudaMemcpy(c->d_sendMask2, mask2.data(), mask2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->d_sendDst2, dst2.size() * sizeof(int32_t)));
+        CUDA_OK(cudaMemcpy(c->d_sendDst2, dst2.data(), dst2.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (!c->d_peerCounter) {
+        CUDA_OK(cudaMalloc(&c->d_peerCounter, sizeof(unsigned)));
+        CUDA_OK(cudaMemset(c->d_peerCounter, 0, sizeof(unsigned)));
+    }
+    c->peerPad = pad;
+    c->peerBlocks = blocks;
+    c->peerFused = true;
+    return 0;
+}
 // one mapping per handle and process (a 2-rank ring reaches the same peer through both faces)
 int openIpc(const unsigned char *handle64, void **out)
 {
@@ -2030,6 +2246,16 @@ void preloadStepKernels(bool twoField)
     preloadKernel(collideStreamKernel<L, COLL_BGK, true, true, IDX>);
     preloadKernel(collideStreamKernel<L, COLL_TRT, true, false, IDX>);
     preloadKernel(collideStreamKernel<L, COLL_TRT, true, true, IDX>);
+    if constexpr (IDX == IDX_COMPACT) {
+        preloadKernel(collideStreamKernel<L, COLL_BGK, false, false, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_BGK, false, true, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, false, false, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, false, true, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_BGK, true, false, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_BGK, true, true, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, true, false, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, true, true, IDX_COMPACT, true>);
+    }
     preloadKernel(massChangeKernel<L, IDX>);
     if constexpr (L::id != D3Q27::id) {
         if (twoField) {
@@ -2149,11 +2375,19 @@ int chimp_local_pointers(chimp_lattice *c, void **out3)
     return 0;
 }
 
+int chimp_peer_mode(chimp_lattice *c, char *why, int why_len)
+{
+    if (!c) return 0;
+    if (why && why_len > 0) snprintf(why, (size_t)why_len, "%s", c->peerWhy.c_str());
+    return !c->peerHalos ? 0 : c->peerFused ? 2 : 1;
+}
+
 int chimp_set_boundary_count(chimp_lattice *c, int n_boundary)
 {
     if (check(c, true)) return 1;
     if (n_boundary < 0 || n_boundary > c->n) return fail("boundary count out of range");
     c->nBoundary = std::min(((n_boundary + 31) / 32) * 32, c->n);
+    if (c->peerHalos && buildPeerTables(c)) return 1;
     return 0;
 }
 int chimp_set_exchange_callback(chimp_lattice *c, chimp_exchange_fn fn, void *user)
@@ -2200,7 +2434,7 @@ int chimp_synchronize(chimp_lattice *c)
     CUDA_OK(cudaSetDevice(c->device));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaStreamSynchronize(c->haloStream));
-    return 0;
+    return checkDeviceError(c);
 }
 
 // ---- introspection ------------------------------------------------------------------------

@@ -51,10 +51,9 @@ __global__ void haloPushKernel(double *peerX, const double *__restrict__ X, cons
     }
 }
 
-__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect)
+__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect, unsigned long long timeoutNs, unsigned *error)
 {
-    const volatile unsigned long long *f = flag;
-    while (*f < expect) __nanosleep(200);
+    awaitCounter(flag, expect, timeoutNs, error, 1u);
     __threadfence_system();
 }
 
@@ -115,17 +114,15 @@ __global__ void foldAndPushKernel(const double *__restrict__ partial, int nBlock
 // obtains the same bits -- and forms F_x = 2 (momx - sum / nGlobal) (main_TWOPHASE.cpp:301-308)
 __global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
                                   double *sumOut, double *forceX, const unsigned long long *flags, unsigned flagMask,
-                                  unsigned long long flagExpect)
+                                  unsigned long long flagExpect, unsigned long long timeoutNs, unsigned *error)
 {
     const MailSlotDev *slots = (const MailSlotDev *)mail + parity * 64;
     const int w = threadIdx.x;
     if (w < world) {
-        const volatile unsigned long long *f = &slots[w].seq;
-        while (*f < seq) __nanosleep(100);
+        awaitCounter(&slots[w].seq, seq, timeoutNs, error, 2u);
     } else if (w >= 64 && ((flagMask >> (w - 64)) & 1u)) {
         // threads 64.. also wait for the arrival counters of the scalar halo (one launch instead of three)
-        const volatile unsigned long long *f = flags + (w - 64);
-        while (*f < flagExpect) __nanosleep(100);
+        awaitCounter(flags + (w - 64), flagExpect, timeoutNs, error, 3u);
     }
     __threadfence_system();
     __syncthreads();
@@ -164,13 +161,11 @@ __global__ void tilePhiRangesKernel(const int32_t *__restrict__ ptable, int n, i
 }
 
 // waits until every arrival counter selected by `mask` (bit k -> flags[k]) has reached `expect`
-__global__ void waitFlagsKernel(const unsigned long long *flags, unsigned mask, unsigned long long expect)
+__global__ void waitFlagsKernel(const unsigned long long *flags, unsigned mask, unsigned long long expect, unsigned long long timeoutNs,
+                                unsigned *error)
 {
     const unsigned k = threadIdx.x;
-    if ((mask >> k) & 1u) {
-        const volatile unsigned long long *f = flags + k;
-        while (*f < expect) __nanosleep(100);
-    }
+    if ((mask >> k) & 1u) awaitCounter(flags + k, expect, timeoutNs, error, 1u);
     __threadfence_system();
 }
 
@@ -201,7 +196,7 @@ __global__ void massFinalizeKernel(const double *__restrict__ partial, int nBloc
 // Folds the per-block x-momentum partials in a fixed order.  finish == 0: only the local sum is
 // written (an all-reduce over ranks follows); finish == 1: partial[] already holds the global
 // sum(s) and F_x = 2 (momx - sum / nGlobal) is produced (main_TWOPHASE.cpp:299-308).
-__global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks, double momx, double nGlobal,
+__global__ void fluxForceKernel(const double *partial, int nBlocks, double momx, double nGlobal,
                                 double *sumOut, double *forceX, int finish)
 {
     __shared__ double sh[8];

@@ -67,6 +67,57 @@ struct Planes {
     double *out[27];         // field 0, plane q of the buffer being written
 };
 
+// Peer halos fused into the step (the MPI ghost exchange of LBmonlatmpi.h:236-297 over NVLink): the first `blocks`
+// thread blocks of a launch hold the halo-coupled nodes.  They wait in their prologue until every face's arrival
+// counter says the neighbours' stores of the previous step have landed (and that the neighbours are done reading the
+// slots written now), store each outgoing population straight into the neighbour GPU's halo-in slot next to the local
+// store, and the last of them to finish publishes the step number in the neighbours' counters.
+constexpr int kMaxFaces = 8;
+struct PeerView {
+    int blocks;                          // 0: plain launch
+    int nFaces;
+    int pad;                             // row length of `dst`
+    const uint32_t *mask;                // [pad] bit q: X[q][i] also goes to a neighbour
+    const int32_t *dst;                  // [nQ][pad] face << 28 | slot inside the neighbour's plane q
+    const uint32_t *mask2;               // optional second destination of the same population (the reference's exchange
+    const int32_t *dst2;                 //   lists name a node once per ghost image of it, LBbndmpi.h:207-315)
+    double *out[kMaxFaces];              // the neighbours' buffers being written (field 0, plane 0)
+    long long stride[kMaxFaces];         // their plane strides
+    unsigned long long *flagOut[kMaxFaces]; // their arrival counters for my faces
+    const unsigned long long *flagIn;    // my arrival counters, one per face
+    unsigned long long expect, publish;  // step numbers: wait for >= expect, publish `publish`
+    unsigned *counter;                   // blocks finished (reset by the last one)
+    unsigned *error;                     // host-mapped error word (arrival timeout)
+    unsigned long long timeoutNs;
+    unsigned long long *trace;           // optional [4]: first block start, publish time, longest wait, last block end (ns)
+};
+
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// bounded spin on an arrival counter; a peer that never arrives raises the error word instead of hanging the job
+__device__ __forceinline__ unsigned long long awaitCounter(const unsigned long long *flag, unsigned long long expect,
+                                                           unsigned long long timeoutNs, unsigned *error, unsigned code)
+{
+    const volatile unsigned long long *f = flag;
+    if (*f >= expect) return 0ull;
+    const unsigned long long t0 = globalTimerNs();
+    unsigned long long waited = 0ull;
+    while (*f < expect) {
+        __nanosleep(100);
+        waited = globalTimerNs() - t0;
+        if (waited > timeoutNs) {
+            if (error) { *(volatile unsigned *)error = code; __threadfence_system(); }
+            break;
+        }
+    }
+    return waited;
+}
+
 struct StepArgs {
     Planes pl;
     long long stride;   // doubles per (field,q) plane
@@ -88,6 +139,7 @@ struct StepArgs {
     // optional outputs
     double *rho; // [nPad]
     double *vel; // [nD][nPad]
+    PeerView peer;
 };
 
 // runtime-q weight lookup for the rare boundary branch (folds when q is a constant)
@@ -176,17 +228,32 @@ struct Gather {
 // / anti-bounce-back pressure links (one_phase variant), optional moment output.
 // Reference loop bodies: std_case/main.cpp:110-135, std_one_phase/main.cpp:534-575.
 // ---------------------------------------------------------------------------------------
-template <class L, int COLL, bool ONEPHASE, bool MOM, int IDX>
+template <class L, int COLL, bool ONEPHASE, bool MOM, int IDX, bool PEER = false>
 __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKernel(const StepArgs a)
 {
     const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.end;
-    if (IDX == IDX_TABLE && !live) return;
-    if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return; // whole warp out of range
+    const bool peerBlock = PEER && (int)blockIdx.x < a.peer.blocks;
+    if (!peerBlock) {
+        if (IDX == IDX_TABLE && !live) return;
+        if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return; // whole warp out of range
+    }
+    uint32_t sendMask = 0, sendMask2 = 0;
+    if (PEER && peerBlock) {
+        if (a.peer.trace && blockIdx.x == 0 && threadIdx.x == 0) a.peer.trace[0] = globalTimerNs();
+        if ((int)threadIdx.x < a.peer.nFaces) {
+            const unsigned long long w = awaitCounter(a.peer.flagIn + threadIdx.x, a.peer.expect, a.peer.timeoutNs, a.peer.error, 1u);
+            if (a.peer.trace && w) atomicMax(a.peer.trace + 2, w);
+        }
+        __syncthreads();
+        sendMask = live ? __ldg(a.peer.mask + i) : 0u;
+        if (a.peer.mask2) sendMask2 = live ? __ldg(a.peer.mask2 + i) : 0u;
+    }
 
     double f[L::nQ];
-    Gather<L, IDX>::load(a, 0ll, i, live, f);
-    if (!live) return;
+    if (!PEER || (i & ~31) < a.end) Gather<L, IDX>::load(a, 0ll, i, live, f);
+    if (!PEER && !live) return;
+    if (!PEER || live) {
 
     double rho = nodeRho<L>(f);
     double F[3] = {a.F[0], a.F[1], a.F[2]};
@@ -228,6 +295,16 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
             v = -v + 2 * chimp_w<L>(q) * a.rhoW * (1 + 0.5 * (kC4Inv * cu * cu - kC2Inv * u2));
         }
         a.pl.out[q][i] = v;
+        if (PEER && ((sendMask >> q) & 1u)) {
+            const int d = __ldg(a.peer.dst + ((unsigned)q * (unsigned)a.peer.pad + (unsigned)i));
+            const int k = d >> 28;
+            a.peer.out[k][(long long)q * a.peer.stride[k] + (d & 0x0fffffff)] = v;
+            if ((sendMask2 >> q) & 1u) {
+                const int d2 = __ldg(a.peer.dst2 + ((unsigned)q * (unsigned)a.peer.pad + (unsigned)i));
+                const int k2 = d2 >> 28;
+                a.peer.out[k2][(long long)q * a.peer.stride[k2] + (d2 & 0x0fffffff)] = v;
+            }
+        }
     };
     auto pairBody = [&](auto pc) {
         constexpr int q = decltype(pc)::value, r = q + L::nPairs;
@@ -291,6 +368,24 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
         }
         finish(q, v, 0.0);
     }
+
+    } // live
+    if (PEER && peerBlock) {
+        // every thread's remote stores are ordered before the counter: fence, count blocks, the last one publishes
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(a.peer.counter, 1u);
+            if (done == (unsigned)a.peer.blocks - 1u) {
+                *a.peer.counter = 0u;
+                __threadfence_system();
+                for (int k = 0; k < a.peer.nFaces; ++k) *(volatile unsigned long long *)a.peer.flagOut[k] = a.peer.publish;
+                __threadfence_system();
+                if (a.peer.trace) a.peer.trace[1] = globalTimerNs();
+            }
+        }
+    }
+    if (PEER && a.peer.trace && threadIdx.x == 0) atomicMax(a.peer.trace + 3, globalTimerNs());
 }
 
 // ---------------------------------------------------------------------------------------
@@ -386,7 +481,7 @@ __global__ void __launch_bounds__(256, CHIMP_PM_MIN_BLOCKS) phaseMomentsKernel(c
     if (threadIdx.x == 0) a.partial[blockIdx.x] = s;
 }
 
-__global__ void fluxForceKernel(const double *__restrict__ partial, int nBlocks, double momx, double nGlobal,
+__global__ void fluxForceKernel(const double *partial, int nBlocks, double momx, double nGlobal,
                                 double *sumOut, double *forceX, int finish);
 
 // Library form of the flux controller (LBglobalforcing.h:8-33): per-block partial sums of
@@ -601,14 +696,15 @@ __global__ void haloPushKernel(double *peerX, const double *__restrict__ X, cons
                                const long long *__restrict__ dst, int count, int nFields, long long fieldStride,
                                long long peerFieldStride, unsigned *blockCounter, unsigned long long *peerFlag,
                                unsigned long long value);
-__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect);
+__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect, unsigned long long timeoutNs, unsigned *error);
 // one double per rank summed over all ranks through peer memory (kernels.cu)
 __global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
                                   double *sumOut, double *forceX, const unsigned long long *flags, unsigned flagMask,
-                                  unsigned long long flagExpect);
+                                  unsigned long long flagExpect, unsigned long long timeoutNs, unsigned *error);
 __global__ void foldAndPushKernel(const double *__restrict__ partial, int nBlocks, double *sumOut, void *const *peerMail, int rank,
                                   int world, int parity, unsigned long long seq);
-__global__ void waitFlagsKernel(const unsigned long long *flags, unsigned mask, unsigned long long expect);
+__global__ void waitFlagsKernel(const unsigned long long *flags, unsigned mask, unsigned long long expect, unsigned long long timeoutNs,
+                                unsigned *error);
 
 // halo pack: buf[k] = X[src[k]] ; unpack: X[dst[k]] = buf[k]   (64-bit slot offsets)
 __global__ void haloPackKernel(double *__restrict__ buf, const double *__restrict__ X,

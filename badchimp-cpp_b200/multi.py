@@ -167,11 +167,14 @@ def peer_memory_available(local, world, device):
     return bool(t.item() == 1.0)
 
 
-def balanced_cuts(my_layer_counts, world):
+def balanced_cuts(my_layer_counts, world, thickness=None):
     """z cut planes such that every rank owns (nearly) the same number of fluid nodes: my_layer_counts holds the
-    fluid nodes of each z-layer of this rank's equal-thickness slab (int64 tensor on the rank's device)"""
+    fluid nodes of each z-layer of this rank's slab (int64 tensor on the rank's device, the same length on every
+    rank; thickness[k] = number of valid leading entries of rank k when the slabs are not equally thick)"""
     all_layers = [torch.zeros_like(my_layer_counts) for _ in range(world)]
     dist.all_gather(all_layers, my_layer_counts)
+    if thickness is not None:
+        all_layers = [a[: int(t)] for a, t in zip(all_layers, thickness)]
     cum = torch.cumsum(torch.cat(all_layers), 0).cpu().numpy()
     targets = cum[-1] * np.arange(1, world) / world
     cuts = [0]
@@ -180,132 +183,26 @@ def balanced_cuts(my_layer_counts, world):
         below = cum[k - 1] if k > 0 else 0
         cuts.append(k if (t - below) < (cum[k] - t) else k + 1)
     cuts.append(len(cum))
+    for k in range(1, len(cuts)):                 # every rank keeps at least one layer
+        cuts[k] = max(cuts[k], cuts[k - 1] + 1)
     return cuts
 
 
-def run_weak_scaling(args, pkg, ingest, size, lattice, tau, force):
-    """bench.py --gpus N (N > 1): every rank owns one size^3 block of a size x size x (size N) pack"""
-    from . import bench_impl as B
-    capi = pkg.capi
-    rank, world = dist.get_rank(), dist.get_world_size()
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    device = torch.device("cuda", local)
-    t_setup = time.perf_counter()
-    gshape = (size, size, size * world)
-    z0, z1 = rank * size, (rank + 1) * size
-    ext = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, z0 - 1, z1 + 1)
-    if getattr(args, "balance", True):
-        # cut planes chosen so that every rank owns the same number of fluid nodes (the step time is the
-        # maximum over ranks; equal-thickness slabs of a random pack differ by several per cent)
-        layers = torch.from_numpy(ext[:, :, 1:-1].reshape(-1, size).sum(axis=0).astype(np.int64)).to(device)
-        cuts = balanced_cuts(layers, world)
-        z0, z1 = cuts[rank], cuts[rank + 1]
-        ext = ingest.sphere_pack_slab(gshape, size / 8.0, 0.35, 1234, z0 - 1, z1 + 1)
-    slab = ingest.build_slab_tables(torch.from_numpy(ext).to(device).bool(), lattice, boundary_first=True)
-    index_form = capi.INDEX_COMPACT if args.index == "compact" else capi.INDEX_TABLE
-    lat = capi.lattice_from_device_table(lattice, slab["n"], slab["n_pad"], slab["n_halo"], slab["table"].data_ptr(),
-                                         slab["labels"].data_ptr(), 1, index_form, local)
-    halo_mode = getattr(args, "halo", "peer")
-    if halo_mode == "peer" and not peer_memory_available(local, world, device):
-        halo_mode = "nccl"   # no peer addressing between the GPUs of this node
-    if halo_mode == "peer":
-        attach_ring_peer(lat, slab, rank, world)
-        halo_bytes = 8.0 * (len(slab["faces"]["down"][0]) + len(slab["faces"]["up"][0]))
-    else:
-        attach_ring(lat, slab, rank, world, device)
-        halo_bytes = 8.0 * (sum(lat._ring.counts[0::2]))
-    n = slab["n"]
-    slab["table"] = slab["labels"] = None
-    torch.cuda.empty_cache()
-    lat.init_uniform(1.0)
-    setup_s = time.perf_counter() - t_setup
+def attach_allreduce(lat, device):
+    """MPI_Allreduce(SUM) of a few doubles in place on the device (mass change per interior domain,
+    std_one_phase/main.cpp:528) over torch.distributed, on the stream the engine hands to the callback"""
+    scratch = torch.zeros(64, dtype=torch.float64, device=device)
+    cuda = device.type == "cuda"
+    rt = C.CDLL("libcudart.so") if cuda else None
+    if rt is not None:
+        rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
 
-    def total(x, op=dist.ReduceOp.SUM):
-        t = torch.tensor([float(x)], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=op)
-        return float(t.item())
+    def on_allreduce(dev_ptr, count, stream_ptr):
+        assert count <= scratch.numel()
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr)):
+            assert rt.cudaMemcpyAsync(scratch.data_ptr(), dev_ptr, 8 * count, 3, stream_ptr) == 0
+            dist.all_reduce(scratch[:count])
+            assert rt.cudaMemcpyAsync(dev_ptr, scratch.data_ptr(), 8 * count, 3, stream_ptr) == 0
 
-    n_total = total(n)
-    lat.step_single(args.warmup, tau=tau, force=force)
-    lat.synchronize()
-    samples, stop = [], threading.Event()
-    th = threading.Thread(target=B._clock_sampler, args=(stop, samples), daemon=True)
-    if rank == 0:
-        th.start()
-    dist.barrier()
-    torch.cuda.synchronize()
-    l1 = capi.lib().chimp_launch_count()
-    ms = lat.step_timed(args.steps, tau=tau, force=force)
-    lat.synchronize()
-    l2 = capi.lib().chimp_launch_count()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms_max = total(ms, dist.ReduceOp.MAX)
-    per_rank = torch.zeros(world, 3, dtype=torch.float64, device=device)
-    per_rank[rank] = torch.tensor([float(n), float(ms) / args.steps, float(z1 - z0)], dtype=torch.float64, device=device)
-    dist.all_reduce(per_rank)
-    per_rank = per_rank.cpu().numpy()
-    if rank == 0:
-        t_extra = time.perf_counter()
-        while len(samples) < 6 and time.perf_counter() - t_extra < 2.0:
-            time.sleep(0.1)
-    # keep all ranks in step while rank 0 samples clocks under load
-    lat.step_single(20, tau=tau, force=force)
-    lat.synchronize()
-    stop.set()
-    rho, _ = lat.download_moments_device_order()
-    mass_err = abs(total(rho.sum()) / n_total - 1.0)
-
-    # end to end per rank: upload LbField (pinned host, reference AoS rows 0..N), K steps, download rho + vel
-    e2e = None
-    try:
-        nq = len(pkg.geometry.BASIS[lattice])
-        host_f = torch.empty((n + 1, nq), dtype=torch.float64, pin_memory=True)
-        host_f[:] = torch.from_numpy(pkg.cases.lattice_weights(lattice))[None, :]
-        host_rho = torch.empty((n + 1,), dtype=torch.float64, pin_memory=True)
-        host_vel = torch.empty((n + 1, 3), dtype=torch.float64, pin_memory=True)
-        lib = capi.lib()
-        p = lat._single_params(tau, force, None)
-        # one untimed cycle first (first-touch of the pinned pages by the copy engines), like the warm-up steps
-        capi._check(lib.chimp_upload_lbfield(lat.h, C.c_void_p(host_f.data_ptr())))
-        capi._check(lib.chimp_step_single(lat.h, C.byref(p), C.c_int(1)))
-        capi._check(lib.chimp_download_rho(lat.h, C.c_void_p(host_rho.data_ptr()), C.c_int(1)))
-        capi._check(lib.chimp_download_vel(lat.h, C.c_void_p(host_vel.data_ptr())))
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        capi._check(lib.chimp_upload_lbfield(lat.h, C.c_void_p(host_f.data_ptr())))
-        capi._check(lib.chimp_step_single(lat.h, C.byref(p), C.c_int(args.steps)))
-        capi._check(lib.chimp_download_rho(lat.h, C.c_void_p(host_rho.data_ptr()), C.c_int(1)))
-        capi._check(lib.chimp_download_vel(lat.h, C.c_void_p(host_vel.data_ptr())))
-        dt = total(time.perf_counter() - t0, dist.ReduceOp.MAX)
-        e2e = {"value": n_total * args.steps / dt / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": total(host_f.numel() * 8) / args.steps,
-               "d2h_bytes_per_step": total((host_rho.numel() + host_vel.numel()) * 8) / args.steps,
-               "cycle": "per rank: upload LbField (pinned host, reference AoS) + %d steps with halo exchange + download rho, vel; wall clock, max over ranks" % args.steps}
-    except Exception as exc:  # pragma: no cover
-        e2e = {"value": None, "unit": "MLUPS", "error": str(exc)}
-
-    if rank == 0:
-        peak, peak_src = B._peaks()
-        kernel_ms = ms_max / args.steps
-        achieved = B.B_ALG[lattice] * n_total / world / (kernel_ms * 1e-3) / 1e9
-        line = {"metric": "MLUPS", "value": n_total * args.steps / (ms_max * 1e-3) / 1e6, "unit": "MLUPS", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "std_case physics (D3Q19 BGK + Guo force + half-way bounce back), periodic random sphere pack %dx%dx%d (one %d^3 block per GPU, z-slabs), R=%d, seed 1234" % (size, size, size * world, size, size // 8),
-                           "fluid_nodes": n_total, "index_form": args.index, "parallelism": "z-slab x%d, halos overlapped with interior nodes" % world,
-                           "l2_policy": "state per GPU 2 x %.1f GB >> 126 MB L2" % (n * 152 / 1e9),
-                           "halo_bytes_per_step_per_gpu": halo_bytes,
-                           "halo_transport": "peer stores over NVLink from the halo-coupled part of the step (CUDA IPC)" if halo_mode == "peer" else "NCCL send/recv (torch.distributed) between pack and unpack kernels",
-                           "slabs": "balanced by fluid-node count" if getattr(args, "balance", True) else "equal thickness",
-                           "nodes_per_rank": [int(x) for x in per_rank[:, 0]], "ms_per_step_per_rank": [round(float(x), 4) for x in per_rank[:, 1]],
-                           "slab_thickness_per_rank": [int(x) for x in per_rank[:, 2]],
-                           "setup_seconds": setup_s, "mean_rho_error": mass_err},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": B._traffic_gb(lattice, args.index, n_total / world)[0], "traffic_unit": "GB per launch per GPU (ncu dram read+write)",
-                             "peak_source": peak_src, "per": "GPU (mean)"},
-                "e2e": e2e, "gpu_launches": int(l2 - l1), "clocks": B._summarize_clocks(samples)}
-        print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
+    lat.set_allreduce_callback(on_allreduce)
+    lat._scratch_allreduce = scratch

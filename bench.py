@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- MLUPS of the fused collide-and-stream hot path (see DESIGN.md, section Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload W] [--size S]
 
 One "step" = one full iteration (collide, stream, halo, boundary) over the whole lattice.
-Workload at N=1: D3Q19 BGK + Guo force + half-way bounce back in a periodic random sphere
-pack (porosity ~0.35, sphere radius size/8, seed 1234), BASELINE.json configs[2] geometry run
-with the std_case physics of configs[0]; MLUPS counts fluid nodes only.
+Default workload: D3Q19 BGK + Guo force + half-way bounce back in a periodic random sphere
+pack 512^3 (porosity ~0.35, sphere radius size/8, seed 1234), BASELINE.json configs[2] geometry run
+with the std_case physics of configs[0]; MLUPS counts fluid nodes only.  With --gpus N (under torchrun)
+the same pack is split into N z-slabs (strong scaling); the weak-scaling number is reported next to it.
+--workload selects the other BASELINE.json configurations (trt, one_phase, d2q9_channel, twophase,
+d3q27_dense); every line carries roofline, e2e, clocks and a parity probe against the oracle.
 """
 import argparse
 import os
@@ -25,6 +28,13 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="edge length of the cubic sphere pack (0 = default)")
     ap.add_argument("--index", default="compact", choices=["compact", "table"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="std_case", choices=["std_case", "trt", "one_phase", "d2q9_channel", "twophase", "d3q27_dense"])
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N>1: split one lattice (strong) or one block per GPU (weak); default per workload")
+    ap.add_argument("--interior-domains", action="store_true", help="one_phase: two interior domains with mass sources (per-step mass-change sum)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity probe against the oracle port before timing")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the secondary weak-scaling measurement")
+    ap.add_argument("--no-traffic", action="store_true", help="N=1: skip the ncu child run that measures DRAM traffic of one step")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N>1: halo transport")
     ap.add_argument("--no-balance", dest="balance", action="store_false", help="N>1: equal-thickness z-slabs instead of equal fluid-node counts")
     args = ap.parse_args()
@@ -32,7 +42,9 @@ def main():
     helpers.load_package()
     import importlib
     bench_impl = importlib.import_module("badchimp_cpp_b200.bench_impl")
-    if args.impl == "reference":
+    if args.traffic_probe:
+        bench_impl.run_traffic_probe(args)
+    elif args.impl == "reference":
         bench_impl.run_reference(args)
     else:
         bench_impl.run_b200(args)

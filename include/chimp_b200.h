@@ -151,6 +151,8 @@ typedef struct {
 } chimp_twophase_params;
 int chimp_set_twophase_density(chimp_lattice *, const double *rho_sca2); /* ScalarField rho(2,size) incl. wall rows */
 int chimp_step_twophase(chimp_lattice *, const chimp_twophase_params *, int n_steps);
+/* same, bracketed by CUDA events on the engine's stream; *ms = device time of the n_steps */
+int chimp_step_twophase_timed(chimp_lattice *, const chimp_twophase_params *, int n_steps, double *ms);
 int chimp_download_phase_field(chimp_lattice *, double *cg_sca);
 double chimp_last_flux_force(chimp_lattice *);
 
@@ -207,6 +209,9 @@ int chimp_local_pointers(chimp_lattice *, void **out3);
 int chimp_connect_peer(chimp_lattice *, int k, const unsigned char *peer_handles192, int same_process,
                        void *const *peer_ptrs3, long long peer_field_stride, int peer_face, long long n_dst,
                        const long long *peer_dst);
+/* 0: no peer halos; 1: peer halos through separate push launches; 2: fused into the step kernel (one launch per step).
+ * `why` receives the reason when the fused form could not be used. */
+int chimp_peer_mode(chimp_lattice *, char *why, int why_len);
 /* Two-phase lattices over peer memory: additionally the scalar halo of phi is stored into the neighbours' ghost slots
  * and the momentum sum of the flux controller (MPI_Allreduce, main_TWOPHASE.cpp:299) travels through a mailbox every rank
  * exports: chimp_ipc_handles_twophase gives 2 x 64-byte handles (phi array, mailbox); chimp_connect_peer_scalar (after

@@ -106,6 +106,23 @@ def main():
           % (rank, slab["n"], steps, ok, np.abs(rho - grho[gslot]).max(), np.abs(vel - gvel[:, gslot]).max(), force, gforce), flush=True)
     ok_all = ok_all and ok
     lat.close()
+    # the bench workloads on N z-slabs against the ORACLE PORT of the undecomposed geometry (the probe bench.py
+    # runs before timing): same ingest, halo transport and step kernels as the timed runs
+    bench_impl = importlib.import_module("badchimp_cpp_b200.bench_impl")
+    W = importlib.import_module("badchimp_cpp_b200.workloads")
+    halo = os.environ.get("CHIMP_HALO", "peer")
+    for workload, interior in (("std_case", False), ("trt", False), ("one_phase", False), ("one_phase", True), ("twophase", False),
+                               ("d3q27_dense", False)):
+        wl = W.WORKLOADS[workload]
+        try:
+            res = bench_impl.parity_probe(pkg, ingest, multi, wl, workload, rank, world, dev, capi.INDEX_COMPACT, halo, interior)
+            ok = True
+        except SystemExit as exc:
+            res, ok = str(exc), False
+        if rank == 0:
+            print("workload %s%s on %d ranks vs oracle port: %s" % (workload, " +interior domains" if interior else "", world, res), flush=True)
+        ok_all = ok_all and ok
+        dist.barrier()
     t = torch.tensor([1.0 if ok_all else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -432,11 +432,24 @@ def test_step_argument_errors():
         lat.finalize(1)                          # twice
 
 
+def _connect_in_process(lats):
+    for r, lat in enumerate(lats):
+        for k in range(lat.num_neighbors()):
+            nr = lat.neighbor_info(k)[0]
+            other = lats[nr]
+            ko = [j for j in range(other.num_neighbors()) if other.neighbor_info(j)[0] == r][0]
+            lat.connect_peer(k, other.nq * other.plane_stride(), ko, other.recv_dst(ko), pointers=other.local_pointers())
+
+
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", ["std_d3q19_p3", "std_d3q27_p2", "std_d2q9_pack_p2"])
-def test_peer_halos_bit_exact_vs_reference(name):
+def test_peer_halos_bit_exact_vs_reference(name, fused, monkeypatch):
     """peer path: every rank stores its outgoing populations straight into the neighbours' halo-in slots
-    and publishes an arrival counter (no pack / transport / unpack); N contexts in one process connect
-    through raw device pointers, N processes through CUDA IPC handles (tests/multi_gpu_check.py)"""
+    and publishes an arrival counter (no pack / transport / unpack) -- from inside the step kernel, whose first
+    blocks hold the halo-coupled nodes (fused, the default), or from separate push launches (CHIMP_PEER_FUSED=0).
+    N contexts in one process connect through raw device pointers, N processes through CUDA IPC handles
+    (tests/multi_gpu_check.py)"""
+    monkeypatch.setenv("CHIMP_PEER_FUSED", "1" if fused else "0")
     g = helpers.Golden(name)
     pkg = helpers.load_package()
     lg, tabs = helpers.build_tables(g)
@@ -444,24 +457,44 @@ def test_peer_halos_bit_exact_vs_reference(name):
     for lat, t in zip(lats, tabs):
         lat.finalize(1, True)
         lat.upload(pkg.cases.std_case_initial_state(t, g.attr("init_rho"))[0])
-    for r, lat in enumerate(lats):
-        for k in range(lat.num_neighbors()):
-            nr = lat.neighbor_info(k)[0]
-            other = lats[nr]
-            ko = [j for j in range(other.num_neighbors()) if other.neighbor_info(j)[0] == r][0]
-            lat.connect_peer(k, other.nq * other.plane_stride(), ko, other.recv_dst(ko), pointers=other.local_pointers())
+    _connect_in_process(lats)
+    for lat in lats:
+        assert lat.peer_mode() == ((2, "") if fused else (1, "switched off (CHIMP_PEER_FUSED=0)")), lat.peer_mode()
+    lib = pkg.capi.lib()
     a = g.args
     done = 0
     for step in [s for s in g.dump if s > 0]:
+        l0 = lib.chimp_launch_count()
         for _ in range(step - done):
             for lat in lats:
                 lat.step_begin(tau=a.get("tau", 0.8), force=g.force())
             for lat in lats:
                 lat.step_end()
+        if fused:   # one launch per rank and step: exchange and counters live inside the step kernel
+            assert lib.chimp_launch_count() - l0 == (step - done) * len(lats)
         done = step
         for r, (lat, t) in enumerate(zip(lats, tabs)):
             bulk = t.bulk_nodes()
             assert np.array_equal(lat.download()[bulk], g.f(r, step)[bulk]), "rank %d step %d" % (r, step)
+
+
+def test_peer_that_never_arrives_raises_an_error_instead_of_hanging(monkeypatch):
+    """bounded device-side waits: a rank whose neighbour stops stepping gets an error from the next synchronising
+    call (CHIMP_PEER_TIMEOUT_MS), not a hung GPU"""
+    monkeypatch.setenv("CHIMP_PEER_TIMEOUT_MS", "300")
+    g = helpers.Golden("std_d3q19_p3")
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    lats = build_engine_tables(g, lg, tabs, True)
+    for lat, t in zip(lats, tabs):
+        lat.finalize(1, True)
+        lat.upload(pkg.cases.std_case_initial_state(t, g.attr("init_rho"))[0])
+    _connect_in_process(lats)
+    lats[0].step_single(1, tau=0.8, force=g.force())     # step 1 needs nothing from the neighbours
+    lats[0].synchronize()
+    lats[0].step_single(1, tau=0.8, force=g.force())     # step 2 waits for their step 1, which never comes
+    with pytest.raises(pkg.capi.ChimpError, match="did not arrive"):
+        lats[0].synchronize()
 
 
 def test_mass_flux_through_pressure_nodes_and_flux_force():
