@@ -174,8 +174,9 @@ struct chimp_lattice {
     // peer exchange fused into the step kernel (PeerView): per halo-coupled node the directions that leave the rank
     // and where they land; built once every face is connected
     bool peerFused = false;
-    uint32_t *d_sendMask = nullptr, *d_sendMask2 = nullptr;
-    int32_t *d_sendDst = nullptr, *d_sendDst2 = nullptr;
+    uint32_t *d_sendMask = nullptr;
+    int32_t *d_sendDst = nullptr, *d_extraStart = nullptr;
+    int2 *d_extra = nullptr;
     int peerPad = 0, peerBlocks = 0;
     unsigned *d_peerCounter = nullptr;
     unsigned *h_error = nullptr, *d_error = nullptr; // host-mapped error word raised by a device-side arrival timeout
@@ -885,7 +886,7 @@ void chimp_destroy(chimp_lattice *c)
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
     freeDev(c->d_rho); freeDev(c->d_vel); freeDev(c->d_flags); freeDev(c->d_slotOf);
     freeDev(c->d_mail); freeDev(c->d_peerMail);
-    freeDev(c->d_sendMask); freeDev(c->d_sendDst); freeDev(c->d_sendMask2); freeDev(c->d_sendDst2);
+    freeDev(c->d_sendMask); freeDev(c->d_sendDst); freeDev(c->d_extraStart); freeDev(c->d_extra);
     freeDev(c->d_peerCounter); freeDev(c->d_trace);
     if (c->h_error) cudaFreeHost(c->h_error);
     freeDev(c->d_tpSeq); freeDev(c->d_tpDeps); freeDev(c->d_tpDone); freeDev(c->d_tpTicket); freeDev(c->d_tpMom);
@@ -1193,8 +1194,8 @@ int stepBegin(chimp_lattice *c, const chimp_single_params *p, bool mom, bool cal
         pv.pad = c->peerPad;
         pv.mask = c->d_sendMask;
         pv.dst = c->d_sendDst;
-        pv.mask2 = c->d_sendMask2;
-        pv.dst2 = c->d_sendDst2;
+        pv.extraStart = c->d_extraStart;
+        pv.extra = c->d_extra;
         const int outIdx = c->cur ^ 1;
         for (int k = 0; k < pv.nFaces; ++k) {
             const Neighbor &nb = c->nbrs[k];
@@ -2143,7 +2144,7 @@ namespace {
 int buildPeerTables(chimp_lattice *c)
 {
     c->peerFused = false;
-    freeDev(c->d_sendMask); freeDev(c->d_sendDst); freeDev(c->d_sendMask2); freeDev(c->d_sendDst2);
+    freeDev(c->d_sendMask); freeDev(c->d_sendDst); freeDev(c->d_extraStart); freeDev(c->d_extra);
     c->peerWhy = "";
     auto notFused = [&](const char *why) { c->peerWhy = why; return 0; };
     if (!c->peerFusedEnv) return notFused("switched off (CHIMP_PEER_FUSED=0)");
@@ -2154,8 +2155,9 @@ int buildPeerTables(chimp_lattice *c)
     const int nQ = c->li.nQ;
     const int blocks = (c->nBoundary + CHIMP_BLOCK - 1) / CHIMP_BLOCK;
     const int pad = blocks * CHIMP_BLOCK;
-    std::vector<uint32_t> mask(pad, 0u), mask2;
-    std::vector<int32_t> dst((size_t)nQ * pad, -1), dst2;
+    std::vector<uint32_t> mask(pad, 0u);
+    std::vector<int32_t> dst((size_t)nQ * pad, -1);
+    std::vector<std::pair<int, int2>> more; // (slot, {q, word})
     for (size_t k = 0; k < c->nbrs.size(); ++k) {
         const Neighbor &nb = c->nbrs[k];
         if ((long long)nb.hSrc.size() != nb.sendCount || (long long)nb.hPeerDst.size() != nb.sendCount) return notFused("send list not available on the host");
@@ -2169,11 +2171,8 @@ int buildPeerTables(chimp_lattice *c)
             if (dslot >= (1ll << 28)) return notFused("peer plane too long for the packed destination word");
             const int32_t word = (int32_t)((k << 28) | dslot);
             if ((mask[slot] >> q) & 1u) {
-                // the reference's lists name a node once per ghost image the receiver holds of it: second destination
-                if (mask2.empty()) { mask2.assign(pad, 0u); dst2.assign((size_t)nQ * pad, -1); }
-                if ((mask2[slot] >> q) & 1u) return notFused("a population is sent to more than two places");
-                mask2[slot] |= 1u << q;
-                dst2[(size_t)q * pad + slot] = word;
+                // the reference's lists name a node once per ghost image the receiver holds of it: further destinations
+                more.push_back({(int)slot, make_int2((int)q, word)});
                 continue;
             }
             mask[slot] |= 1u << q;
@@ -2184,11 +2183,17 @@ int buildPeerTables(chimp_lattice *c)
     CUDA_OK(cudaMemcpy(c->d_sendMask, mask.data(), mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&c->d_sendDst, dst.size() * sizeof(int32_t)));
     CUDA_OK(cudaMemcpy(c->d_sendDst, dst.data(), dst.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (!mask2.empty()) {
-        CUDA_OK(cudaMalloc(&c->d_sendMask2, mask2.size() * sizeof(uint32_t)));
-        CUDA_OK(cudaMemcpy(c->d_sendMask2, mask2.data(), mask2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMalloc(&c->d_sendDst2, dst2.size() * sizeof(int32_t)));
-        CUDA_OK(cudaMemcpy(c->d_sendDst2, dst2.data(), dst2.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!more.empty()) {
+        std::stable_sort(more.begin(), more.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return x.first < y.first; });
+        std::vector<int32_t> start(pad + 1, 0);
+        std::vector<int2> ent(more.size());
+        for (auto &m : more) ++start[m.first + 1];
+        for (int i = 0; i < pad; ++i) start[i + 1] += start[i];
+        for (size_t e = 0; e < more.size(); ++e) ent[e] = more[e].second;
+        CUDA_OK(cudaMalloc(&c->d_extraStart, start.size() * sizeof(int32_t)));
+        CUDA_OK(cudaMemcpy(c->d_extraStart, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->d_extra, ent.size() * sizeof(int2)));
+        CUDA_OK(cudaMemcpy(c->d_extra, ent.data(), ent.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
     if (!c->d_peerCounter) {
         CUDA_OK(cudaMalloc(&c->d_peerCounter, sizeof(unsigned)));

@@ -79,8 +79,9 @@ struct PeerView {
     int pad;                             // row length of `dst`
     const uint32_t *mask;                // [pad] bit q: X[q][i] also goes to a neighbour
     const int32_t *dst;                  // [nQ][pad] face << 28 | slot inside the neighbour's plane q
-    const uint32_t *mask2;               // optional second destination of the same population (the reference's exchange
-    const int32_t *dst2;                 //   lists name a node once per ghost image of it, LBbndmpi.h:207-315)
+    const int32_t *extraStart;           // optional [pad + 1]: further destinations of node i are extra[extraStart[i] .. extraStart[i+1])
+    const int2 *extra;                   //   {q, face << 28 | slot}: the reference's exchange lists name a node once per ghost
+                                         //   image the receiver holds of it (periodic rims, LBbndmpi.h:207-315)
     double *out[kMaxFaces];              // the neighbours' buffers being written (field 0, plane 0)
     long long stride[kMaxFaces];         // their plane strides
     unsigned long long *flagOut[kMaxFaces]; // their arrival counters for my faces
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
         if (IDX == IDX_TABLE && !live) return;
         if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return; // whole warp out of range
     }
-    uint32_t sendMask = 0, sendMask2 = 0;
+    uint32_t sendMask = 0;
     if (PEER && peerBlock) {
         if (a.peer.trace && blockIdx.x == 0 && threadIdx.x == 0) a.peer.trace[0] = globalTimerNs();
         if ((int)threadIdx.x < a.peer.nFaces) {
@@ -247,7 +248,6 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
         }
         __syncthreads();
         sendMask = live ? __ldg(a.peer.mask + i) : 0u;
-        if (a.peer.mask2) sendMask2 = live ? __ldg(a.peer.mask2 + i) : 0u;
     }
 
     double f[L::nQ];
@@ -299,11 +299,6 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
             const int d = __ldg(a.peer.dst + ((unsigned)q * (unsigned)a.peer.pad + (unsigned)i));
             const int k = d >> 28;
             a.peer.out[k][(long long)q * a.peer.stride[k] + (d & 0x0fffffff)] = v;
-            if ((sendMask2 >> q) & 1u) {
-                const int d2 = __ldg(a.peer.dst2 + ((unsigned)q * (unsigned)a.peer.pad + (unsigned)i));
-                const int k2 = d2 >> 28;
-                a.peer.out[k2][(long long)q * a.peer.stride[k2] + (d2 & 0x0fffffff)] = v;
-            }
         }
     };
     auto pairBody = [&](auto pc) {
@@ -369,6 +364,14 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
         finish(q, v, 0.0);
     }
 
+    if (PEER && peerBlock && a.peer.extraStart) {
+        // further copies of populations this thread has just stored (its own stores are visible to it)
+        for (int e = __ldg(a.peer.extraStart + i), e1 = __ldg(a.peer.extraStart + i + 1); e < e1; ++e) {
+            const int2 x = __ldg(a.peer.extra + e);
+            const int k = x.y >> 28;
+            a.peer.out[k][(long long)x.x * a.peer.stride[k] + (x.y & 0x0fffffff)] = a.pl.out[x.x][i];
+        }
+    }
     } // live
     if (PEER && peerBlock) {
         // every thread's remote stores are ordered before the counter: fence, count blocks, the last one publishes
