@@ -95,13 +95,18 @@ def sphere_pack_slab(shape, radius, porosity, seed, z0, z1):
     return geo
 
 
-def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: bool = True, wall_phi_ext: torch.Tensor = None):
+def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: bool = True, wall_phi_ext: torch.Tensor = None,
+                      order: str = "layer"):
     """One rank of a z-slab decomposition (periodic in x, y; z neighbours are other ranks).
 
     fluid_ext: bool [nx, ny, nz + 2]: the rank's own slab plus one halo layer below (index 0) and
     above (index -1) taken from the neighbour ranks.  Own fluid nodes are labelled 1..N in C-order
     (the reference's per-rank numbering, vtklb.py:92-94).  Device slots: nodes of the first and
-    last z-layer first (they are the only halo-coupled ones) when boundary_first.
+    last z-layer first (they are the only halo-coupled ones) when boundary_first.  order = "layer" (default)
+    puts the remaining nodes layer by layer (z slowest, each layer in C-order of (x, y)): the sources of 32
+    consecutive slots then lie close together in EVERY direction, also next to the two leading layers, so the
+    compact index needs (almost) no explicit rows; order = "label" keeps them in label order (z fastest), where
+    every tile that touches the second or the second-to-last layer pulls from the far-away leading slots.
 
     Returns dict(table int32 [nQ, n_pad], labels int32 [n_pad], n, n_pad, n_halo, n_boundary,
     faces = {"down": (send_src, recv_dst), "up": (send_src, recv_dst)}) with int64 slot offsets
@@ -128,14 +133,21 @@ def build_slab_tables(fluid_ext: torch.Tensor, lattice: str, boundary_first: boo
     n_pad = ((n + 31) // 32) * 32
     label = (torch.cumsum(flat, 0, dtype=torch.int32) * flat).reshape(own.shape)
     own_idx = torch.nonzero(flat).reshape(-1)                 # flat cell index of label 1..n
+    z_of = own_idx % nz
     if boundary_first:
-        z_of = own_idx % nz
         is_b = (z_of == 0) | (z_of == nz - 1)
-        order = torch.cat([torch.nonzero(is_b).reshape(-1), torch.nonzero(~is_b).reshape(-1)])  # label-1 per slot
         n_boundary = int(is_b.sum().item())
+        if order == "layer":
+            # tiers: layer 0, layer nz-1, then layers 1 .. nz-2; inside a tier the C-order of (x, y)
+            tier = torch.where(z_of == 0, torch.zeros_like(z_of), torch.where(z_of == nz - 1, torch.ones_like(z_of), z_of + 1))
+            key = tier * (own.shape[0] * own.shape[1]) + own_idx // nz
+            order_idx = torch.argsort(key, stable=True)
+        else:
+            order_idx = torch.cat([torch.nonzero(is_b).reshape(-1), torch.nonzero(~is_b).reshape(-1)])  # label-1 per slot
     else:
-        order = torch.arange(n, device=dev)
+        order_idx = torch.arange(n, device=dev)
         n_boundary = 0
+    order = order_idx
     slot_of_label = torch.full((n + 1,), -1, dtype=torch.int32, device=dev)
     slot_of_label[order + 1] = torch.arange(n, dtype=torch.int32, device=dev)
     slot_grid = slot_of_label[label.long()]                    # -1 on solid cells
