@@ -214,7 +214,7 @@ class _Runner:
         return self.lat.step_timed(k, tau=self.wl["tau"], force=self.wl["force"], trt=self.wl["trt"])
 
 
-def parity_probe(pkg, ingest, multi, wl, workload, rank, world, device, index_form, halo, interior_domains, steps=10):
+def parity_probe(pkg, ingest, multi, wl, workload, rank, world, device, index_form, halo, interior_domains, steps=10, size=None):
     """A small case of the same workload on the same code path (structured ingest, N z-slabs, the same halo
     transport and step kernels) checked against the oracle port of the UNDECOMPOSED geometry on rank 0's host,
     before anything is timed: after one step (the per-step bar: bit-exact for the single-field kernels, <= 1e-12
@@ -225,9 +225,10 @@ def parity_probe(pkg, ingest, multi, wl, workload, rank, world, device, index_fo
     from . import workloads as W
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     scaling = "weak" if wl["scaling"] == "weak" else "strong"
-    size = {"pack": 64, "dense": 24, "channel": 96}[wl["geometry"]]
-    if wl["geometry"] == "pack" and scaling == "strong" and size // world < 2:
-        size = 4 * world
+    if size is None:
+        size = {"pack": 64, "dense": 24, "channel": 96}[wl["geometry"]]
+        if wl["geometry"] == "pack" and scaling == "strong" and size // world < 2:
+            size = 4 * world
     rl = W.build(pkg, ingest, multi, wl, size, rank, world, device, scaling, index_form, halo=halo, balance=True,
                  interior_domains=interior_domains, keep_cells=True)
     run = _Runner(rl, wl)

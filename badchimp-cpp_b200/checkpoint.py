@@ -6,7 +6,12 @@
     .lblbf   int nFields, int nQ, int nNodes,   double[nFields*nQ*nNodes]       (LbField)
 
 Arrays are node-major [node, field, component] exactly as chimp_upload_lbfield / chimp_download_*
-take and return them, so a state written by the CPU code restarts on the GPU and vice versa."""
+take and return them, so a state written by the CPU code restarts on the GPU and vice versa.
+
+Readers take an optional `expect` tuple with the header the caller's lattice needs ((nFields, nQ, nNodes),
+(nFields, nNodes), (nFields, nD, nNodes)); like the reference, which refuses a file whose header does not match the
+field it is read into ("No data read!", LBfield.h:124-131, 260-268, 406-413), a mismatch is an error -- as is a
+truncated file."""
 from __future__ import annotations
 
 import numpy as np
@@ -20,12 +25,23 @@ def write_lbfield(path_prefix, f):
         f.tofile(fh)
 
 
-def read_lbfield(path_prefix):
-    with open(path_prefix + ".lblbf", "rb") as fh:
-        n_fields, nq, n_nodes = np.fromfile(fh, dtype=np.int32, count=3)
-        data = np.fromfile(fh, dtype=np.float64, count=int(n_fields) * int(nq) * int(n_nodes))
-    if data.size != int(n_fields) * int(nq) * int(n_nodes):
-        raise ValueError("truncated LbField file " + path_prefix + ".lblbf")
+def _read(path, n_header, expect, what):
+    with open(path, "rb") as fh:
+        head = np.fromfile(fh, dtype=np.int32, count=n_header)
+        if head.size != n_header or (head <= 0).any():
+            raise ValueError("%s file %s: bad header %s" % (what, path, head.tolist()))
+        header = tuple(int(x) for x in head)
+        if expect is not None and header != tuple(int(x) for x in expect):
+            raise ValueError("%s file %s holds %s, the field needs %s: no data read" % (what, path, header, tuple(expect)))
+        count = int(np.prod([int(x) for x in head], dtype=np.int64))
+        data = np.fromfile(fh, dtype=np.float64, count=count)
+    if data.size != count:
+        raise ValueError("truncated %s file %s: %d of %d values" % (what, path, data.size, count))
+    return header, data
+
+
+def read_lbfield(path_prefix, expect=None):
+    (n_fields, nq, n_nodes), data = _read(path_prefix + ".lblbf", 3, expect, "LbField")
     return data.reshape(n_nodes, n_fields, nq)
 
 
@@ -39,10 +55,8 @@ def write_scalar_field(path_prefix, s):
         s.tofile(fh)
 
 
-def read_scalar_field(path_prefix):
-    with open(path_prefix + ".lbsca", "rb") as fh:
-        n_fields, n_nodes = np.fromfile(fh, dtype=np.int32, count=2)
-        data = np.fromfile(fh, dtype=np.float64, count=int(n_fields) * int(n_nodes))
+def read_scalar_field(path_prefix, expect=None):
+    (n_fields, n_nodes), data = _read(path_prefix + ".lbsca", 2, expect, "ScalarField")
     return data.reshape(n_nodes, n_fields)
 
 
@@ -56,8 +70,6 @@ def write_vector_field(path_prefix, v, n_fields=1):
         v.tofile(fh)
 
 
-def read_vector_field(path_prefix):
-    with open(path_prefix + ".lbvec", "rb") as fh:
-        n_fields, nd, n_nodes = np.fromfile(fh, dtype=np.int32, count=3)
-        data = np.fromfile(fh, dtype=np.float64, count=int(n_fields) * int(nd) * int(n_nodes))
+def read_vector_field(path_prefix, expect=None):
+    (n_fields, nd, n_nodes), data = _read(path_prefix + ".lbvec", 3, expect, "VectorField")
     return data.reshape(n_nodes, n_fields, nd)

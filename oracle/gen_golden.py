@@ -36,7 +36,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attributes, keep_vtklb=False, checkpoint=False, vtk=False,
-                  vtk_ascii=False):
+                  vtk_ascii=False, checkpoint_at=None, extra=()):
     d = tempfile.mkdtemp(prefix="golden_")
     os.makedirs(os.path.join(d, "out"))
     basis = lattice if lattice != "D3Q27" else G.BASIS["D3Q27"].astype(int)
@@ -49,6 +49,9 @@ def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attribu
            str(nranks), "--steps", str(steps), "--dump", ",".join(str(s) for s in dump)] + [str(a) for a in args]
     if checkpoint:
         cmd += ["--checkpoint", os.path.join(OUT, name + ".ckpt")]
+    if checkpoint_at is not None:   # the reference's own writeToFile() after that step; the run goes on
+        cmd += ["--checkpoint", os.path.join(OUT, name + ".ckpt"), "--checkpoint-at", str(checkpoint_at)]
+    cmd += list(extra)
     if vtk:  # the reference's own Output<LT>::write (io/Output.h, io/VTK.h) after the last step
         vdir = os.path.join(OUT, name + ".vtk")
         shutil.rmtree(vdir, ignore_errors=True)
@@ -131,13 +134,35 @@ def vtk_goldens():
                   {"rho0": r2, "rho1": 1.0 - r2, "wettability": 0.3 * (pack2d == 0), "source": np.zeros((9, 8), dtype=int)}, vtk=True)
 
 
+def restart_and_forcing_goldens():
+    """round 2: a restart file written by the reference in the middle of a run (f4), and the reference's own
+    calcFluxForceCartDir / calcCapNumbForceCartDir (LBglobalforcing.h:8-98) evaluated at dump steps (f2)"""
+    shape = (12, 10, 14)
+    pack = G.sphere_pack(shape, 3.2, 0.62, 11).astype(int)
+    ones = np.ones(shape)
+    rho_init = 1.0 + 0.02 * np.sin(2 * np.pi * np.arange(shape[0]) / shape[0])[:, None, None] * ones
+    # same case as std_d3q19_p1 (whose .vtklb file is committed): checkpoint after step 4, dumps at 4 and 10
+    run_reference("restart_d3q19_p1", pack, "D3Q19", "xyz", "std_case", 10, [4, 10], ["--tau", 0.8, "--force", "1e-6,2e-7,-3e-7"],
+                  {"init_rho": rho_init}, checkpoint_at=4, extra=["--no-tables", "--global-forcing", "--fixed-flux", "1e-5"])
+    x = np.arange(shape[0])[:, None, None] * np.ones(shape)
+    rho0 = (x < shape[0] / 2).astype(float)
+    tp_attrs = {"rho0": rho0, "rho1": 1.0 - rho0, "wettability": 0.5 * (pack == 0), "source": np.zeros(shape, dtype=int)}
+    tp_args = ["--tau2", "1.0,0.8", "--sigma", 0.01, "--beta", 1.0, "--momx", 1e-5, "--force", "0,1e-7,0"]
+    run_reference("forcing_twophase_d3q19_p1", pack, "D3Q19", "xyz", "twophase", 5, [1, 3, 5], tp_args, tp_attrs,
+                  extra=["--no-tables", "--no-f", "--global-forcing", "--fixed-flux", "2e-5", "--cap-numb", "1e-4,0.1666666666666666574,0.1"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
     if sys.argv[1:] == ["vtk"]:
         vtk_goldens()
         return
+    if sys.argv[1:] == ["round2"]:
+        restart_and_forcing_goldens()
+        return
     vtk_goldens()
+    restart_and_forcing_goldens()
     shape = (12, 10, 14)
     pack = G.sphere_pack(shape, 3.2, 0.62, 11).astype(int)
     ones = np.ones(shape)

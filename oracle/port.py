@@ -118,6 +118,31 @@ class PortRank:
         return float(F[0])
 
 
+def flux_force(ranks, field_no, cart_dir, fixed_flux, n_nodes_global):
+    """calcFluxForceCartDir (LBglobalforcing.h:8-33) over all ranks: per-rank sequential sums, added in rank order
+    (the in-process MPI shim of oracle/_ref adds them in rank order too)"""
+    lib().port_flux_sum.restype = C.c_double
+    total = 0.0
+    for pr in ranks:
+        t = pr.tables()
+        total += lib().port_flux_sum(C.byref(t), _p(pr.f), C.c_int(field_no), C.c_int(cart_dir))
+    total /= n_nodes_global
+    return 2 * (fixed_flux - total)
+
+
+def cap_numb_force(ranks, cart_dir, sigma_cap_numb, nu0, nu1, n_nodes_global):
+    """calcCapNumbForceCartDir (LBglobalforcing.h:35-98) over all ranks"""
+    sums = np.zeros(4)
+    for pr in ranks:
+        t = pr.tables()
+        out = np.zeros(4)
+        rho = _f64(pr.rho)
+        lib().port_cap_numb_sums(C.byref(t), _p(pr.f), _p(rho), C.c_int(cart_dir), _p(out))
+        sums += out
+    sums /= n_nodes_global
+    return 2 * (sigma_cap_numb - (sums[0] * nu0 + sums[1] * nu1)) / (sums[2] * nu0 + sums[3] * nu1)
+
+
 def exchange_lb_field(ranks, exch, fld=0):
     """MonLatMpi::communicateLbField (LBmonlatmpi.h:236-297) for all rank pairs.
     exch[r] = list over neighbours of dict(rank, send_nodes, send_ndir, send_dirs, recv_nodes, recv_ndir, recv_dirs).

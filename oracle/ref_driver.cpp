@@ -52,6 +52,7 @@
 #include "lbsolver/LBcollision2phase.h"
 #include "lbsolver/LBinitiatefield.h"
 #include "lbsolver/LButilities.h"
+#include "lbsolver/LBglobalforcing.h" // calcFluxForceCartDir / calcCapNumbForceCartDir for the --global-forcing records
 #include "lbsolver/LBvtk.h"
 #include "io/Output.h" // the reference's VTK writer, for the --vtk goldens
 #include "LBd3q27.h"
@@ -66,6 +67,10 @@ struct Opts {
     std::string vtk;        // directory for the reference's own Output<LT>::write() after the last step
     bool vtkAscii = false;  // ... through Output<LT, double, VTK::ASCII>
     std::string checkpoint; // prefix for the reference's own writeToFile() dumps after the last step
+    int checkpointAt = -1;  // ... or after this step instead (the run continues)
+    std::string restart;    // prefix of .lblbf files the reference's own LbField::readFromFile() loads before the first step
+    bool globalForcing = false; // at every dump step: the reference's own calcFluxForceCartDir / calcCapNumbForceCartDir
+    double fixedFlux = 1e-5, sigmaCapNumb = 1e-4, nu0 = 1.0 / 6.0, nu1 = 0.1;
     double tau = 0.8, tauSym = 0.0, tauAnti = 0.0; // TRT when tauSym > 0
     std::vector<double> force{0, 0, 0};
     double tau0 = 1, tau1 = 1, sigma = 0.01, beta = 1, momx = 1e-5; // twophase
@@ -214,9 +219,24 @@ double runStdCase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid,
     for (auto n : bulk)
         for (int q = 0; q < LT::nQ; ++q) f(0, q, n) = LT::w[q] * rho(0, n);
 
+    if (!o.restart.empty()) f.readFromFile(o.restart + std::to_string(vtklb.getRank())); // LBfield.h:394-421
+
     const bool trt = o.tauSym > 0.0;
     const lbBase_t tau = o.tau;
+    int numNodes = (int)bulk.size(), numNodesGlobal = 0;
+    MPI_Allreduce(&numNodes, &numNodesGlobal, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
     auto dump = [&](int step) {
+        if (o.globalForcing && o.dumpSteps.count(step)) { // LBglobalforcing.h:8-33, every rank takes part in its all-reduce
+            std::vector<double> ff(LT::nD);
+            for (int d = 0; d < LT::nD; ++d) ff[d] = calcFluxForceCartDir<LT>(0, f, bulk, d, o.fixedFlux, numNodesGlobal);
+            rec.reals("step" + std::to_string(step) + ".fluxForce", ff);
+        }
+        if (step == o.checkpointAt && !o.checkpoint.empty()) {
+            const std::string p = o.checkpoint + std::to_string(vtklb.getRank());
+            f.writeToFile(p);
+            rho.writeToFile(p);
+            vel.writeToFile(p);
+        }
         if (!o.dumpF || !o.dumpSteps.count(step)) return;
         const std::string s = "step" + std::to_string(step) + ".";
         rec.reals(s + "f", flat(f, sz));
@@ -252,7 +272,7 @@ double runStdCase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid,
         dump(i);
     }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (!o.checkpoint.empty()) { // LBfield.h:102-114, 233-247, 378-392
+    if (!o.checkpoint.empty() && o.checkpointAt < 0) { // LBfield.h:102-114, 233-247, 378-392
         const std::string p = o.checkpoint + std::to_string(vtklb.getRank());
         f.writeToFile(p);
         rho.writeToFile(p);
@@ -480,6 +500,18 @@ double runTwoPhase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid
     if (o.dumpTables) rec.reals("rhoInit", flat(rho, sz));
 
     auto dump = [&](int step) {
+        if (o.globalForcing && o.dumpSteps.count(step)) { // LBglobalforcing.h:8-98 on the state a main holds at this point
+            std::vector<double> ff0(LT::nD), ff1(LT::nD), cap(LT::nD);
+            for (int d = 0; d < LT::nD; ++d) {
+                ff0[d] = calcFluxForceCartDir<LT>(0, f, bulk, d, o.fixedFlux, numNodesGlobal);
+                ff1[d] = calcFluxForceCartDir<LT>(1, f, bulk, d, o.fixedFlux, numNodesGlobal);
+                cap[d] = calcCapNumbForceCartDir<LT>(0, f, rho, bulk, d, o.sigmaCapNumb, o.nu0, o.nu1, numNodesGlobal);
+            }
+            const std::string s = "step" + std::to_string(step) + ".";
+            rec.reals(s + "fluxForce0", ff0);
+            rec.reals(s + "fluxForce1", ff1);
+            rec.reals(s + "capForce", cap);
+        }
         if (!o.dumpF || !o.dumpSteps.count(step)) return;
         const std::string s = "step" + std::to_string(step) + ".";
         rec.reals(s + "f", flat(f, sz));
@@ -628,6 +660,11 @@ int main(int argc, char **argv)
         else if (a == "--no-f") o.dumpF = false;
         else if (a == "--time") o.timing = true;
         else if (a == "--checkpoint") o.checkpoint = next();
+        else if (a == "--checkpoint-at") o.checkpointAt = std::stoi(next());
+        else if (a == "--restart") o.restart = next();
+        else if (a == "--global-forcing") o.globalForcing = true;
+        else if (a == "--fixed-flux") o.fixedFlux = std::stod(next());
+        else if (a == "--cap-numb") { auto v = parseList(next()); o.sigmaCapNumb = v[0]; o.nu0 = v[1]; o.nu1 = v[2]; }
         else if (a == "--vtk") o.vtk = next();
         else if (a == "--vtk-ascii") o.vtkAscii = true;
         else if (a == "--tau") o.tau = std::stod(next());

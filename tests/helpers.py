@@ -64,7 +64,7 @@ class Golden:
         return self.z["attr." + name]
 
     def f(self, rank, step, n_fields=1):
-        nq = int(self.rec(rank, "nQ")[0])
+        nq = {"D2Q9": 9, "D3Q19": 19, "D3Q27": 27}[self.lattice]
         return self.rec(rank, "step%d.f" % step).reshape(-1, n_fields, nq)
 
     def force(self):
