@@ -51,7 +51,8 @@ SYMBOLS = [
     "chimp_num_neighbors", "chimp_neighbor_info", "chimp_send_buffer_dev", "chimp_recv_buffer_dev",
     "chimp_set_exchange_callback", "chimp_set_stream", "chimp_synchronize", "chimp_num_own_nodes",
     "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_irregular_fraction",
-    "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_step_twophase_timed", "chimp_peer_mode", "chimp_init_uniform",
+    "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_step_twophase_timed", "chimp_peer_mode", "chimp_voxel_table_host", "chimp_create_from_voxels",
+    "chimp_voxel_phi_table_host", "chimp_set_phi_table_from_voxels", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
     "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_capillary_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles_twophase", "chimp_local_pointers_twophase", "chimp_connect_peer_scalar", "chimp_connect_world", "chimp_host_scalar_halo_lists", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
@@ -503,6 +504,61 @@ class Lattice:
 
     def index_bytes_per_node(self):
         return float(lib().chimp_index_bytes_per_node(self.h))
+
+
+def _periodic_mask(periodic: str):
+    return sum(1 << k for k, name in enumerate("xyz") if name in periodic.lower())
+
+
+def voxel_table_host(lattice: str, voxels, periodic="xyz"):
+    """host half of the voxel ingest (no CUDA): (table int32 [nQ, n_pad], labels int32 [n_pad], n)"""
+    v = np.ascontiguousarray(voxels, dtype=np.uint8)
+    nx, ny, nz = (list(v.shape) + [1])[:3]
+    n, n_pad = C.c_int(), C.c_int()
+    args = (C.c_int(G.LATTICE_ID[lattice]), C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(v), C.c_int(_periodic_mask(periodic)))
+    _check(lib().chimp_voxel_table_host(*args, C.byref(n), C.byref(n_pad), None, None))
+    nq = len(G.BASIS[lattice])
+    table = np.zeros((nq, n_pad.value), dtype=np.int32)
+    labels = np.zeros(n_pad.value, dtype=np.int32)
+    _check(lib().chimp_voxel_table_host(*args, C.byref(n), C.byref(n_pad), _p(table), _p(labels)))
+    return table, labels, n.value
+
+
+def voxel_phi_table_host(lattice: str, voxels, wall_phi, periodic="xyz"):
+    """host half of the colour-gradient tables: (ptable int32 [nQ, n_pad], n_extra, phi_extra [n_extra])"""
+    v = np.ascontiguousarray(voxels, dtype=np.uint8)
+    w = _f64(wall_phi)
+    nx, ny, nz = (list(v.shape) + [1])[:3]
+    args = (C.c_int(G.LATTICE_ID[lattice]), C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(v), C.c_int(_periodic_mask(periodic)))
+    n_extra = C.c_int()
+    _check(lib().chimp_voxel_phi_table_host(*args, _p(w), C.byref(n_extra), None, None))
+    n = int(np.count_nonzero(v))
+    n_pad = ((n + 31) // 32) * 32
+    ptable = np.zeros((len(G.BASIS[lattice]), n_pad), dtype=np.int32)
+    extra = np.zeros(max(n_extra.value, 1))
+    _check(lib().chimp_voxel_phi_table_host(*args, _p(w), C.byref(n_extra), _p(ptable), _p(extra)))
+    return ptable, n_extra.value, extra[: n_extra.value]
+
+
+def lattice_from_voxels(lattice: str, voxels, periodic="xyz", n_fields=1, index_form=INDEX_COMPACT, device=-1, wall_phi=None):
+    """chimp_create_from_voxels: the route a C / C++ main takes from a raw voxel array to a lattice"""
+    v = np.ascontiguousarray(voxels, dtype=np.uint8)
+    nx, ny, nz = (list(v.shape) + [1])[:3]
+    obj = Lattice.__new__(Lattice)
+    obj.lattice = lattice
+    obj.nq = len(G.BASIS[lattice])
+    obj.nd = G.BASIS[lattice].shape[1]
+    obj.n_nodes = int(np.count_nonzero(v)) + 1
+    obj.n_fields = n_fields
+    obj._cb = None
+    obj.h = C.c_void_p()
+    _check(lib().chimp_create_from_voxels(C.byref(obj.h), G.LATTICE_ID[lattice], C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(v),
+                                          C.c_int(_periodic_mask(periodic)), C.c_int(n_fields), C.c_int(index_form), C.c_int(device)))
+    if wall_phi is not None:
+        w = _f64(wall_phi)
+        _check(lib().chimp_set_phi_table_from_voxels(obj.h, C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(v),
+                                                     C.c_int(_periodic_mask(periodic)), _p(w)))
+    return obj
 
 
 def lattice_from_device_table(lattice: str, n_bulk, n_pad, n_halo, table_ptr, label_ptr, n_fields=1,

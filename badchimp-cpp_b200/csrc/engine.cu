@@ -19,6 +19,7 @@
 #include <climits>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/chimp_b200.h"
@@ -2443,6 +2444,244 @@ int chimp_synchronize(chimp_lattice *c)
 }
 
 // ---- introspection ------------------------------------------------------------------------
+// ---- structured geometry ingest for host code --------------------------------------------------------
+// A raw voxel array becomes the pull table with the reference's numbering (own fluid nodes labelled 1..N in C-order
+// of geo[x][y][z], vtklb.py:92-94; device slot = label - 1) and std_case semantics (half-way bounce back on every
+// link whose upstream cell is solid or lies outside a non-periodic axis, LBhalfwaybb.h:37-63):
+//     T[q][i] = label(pos_i - c_q) - 1   if that cell is fluid,   -1 otherwise.
+// Pure host code, threaded over x; the reference's route (vtklb.py -> ASCII file -> LBvtk, LBvtk.h:221-262) cannot
+// load cases beyond 2 GiB of text (LBvtk.h:194-201).
+extern "C++" {
+namespace {
+struct VoxelGrid {
+    int nd, nx, ny, nz, per[3];
+    const uint8_t *v;
+    long long cells() const { return (long long)nx * ny * nz; }
+    long long at(int x, int y, int z) const { return ((long long)x * ny + y) * nz + z; }
+    // cell index of pos + (dx, dy, dz) or -1 when it leaves a non-periodic axis
+    long long shifted(int x, int y, int z, int dx, int dy, int dz) const
+    {
+        int p[3] = {x + dx, y + dy, z + dz};
+        const int n[3] = {nx, ny, nz};
+        for (int a = 0; a < 3; ++a) {
+            if (p[a] < 0 || p[a] >= n[a]) {
+                if (!per[a]) return -1;
+                p[a] = (p[a] + n[a]) % n[a];
+            }
+        }
+        return at(p[0], p[1], p[2]);
+    }
+};
+
+int voxelGrid(VoxelGrid &g, int lattice, int nx, int ny, int nz, const uint8_t *voxels, int periodicMask)
+{
+    const LatInfo li = latInfo(lattice);
+    if (li.nQ == 0) return fail("unknown lattice id %d", lattice);
+    if (!voxels || nx < 1 || ny < 1 || nz < 1) return fail("bad voxel array");
+    if (li.nD == 2 && nz != 1) return fail("a 2-D lattice takes a voxel array [nx][ny] (nz = 1)");
+    if ((long long)nx * ny * nz >= (1ll << 31)) return fail("voxel array too large for 32-bit cell indices");
+    g = VoxelGrid{li.nD, nx, ny, nz, {periodicMask & 1, (periodicMask >> 1) & 1, li.nD == 3 ? (periodicMask >> 2) & 1 : 1}, voxels};
+    return 0;
+}
+
+void lookupC(int lattice, int q, int c[3])
+{
+    const LatInfo li = latInfo(lattice);
+    for (int d = 0; d < 3; ++d) c[d] = d < li.nD ? chimp_lattice_c(lattice, q, d) : 0;
+}
+
+template <class Fn>
+void parallelOverX(int nx, Fn fn)
+{
+    const int nThreads = std::max(1, std::min<int>(nx, (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()))));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nThreads; ++t)
+        th.emplace_back([=] { fn((int)((long long)nx * t / nThreads), (int)((long long)nx * (t + 1) / nThreads)); });
+    for (auto &x : th) x.join();
+}
+
+// label[cell] = 1..N for fluid cells in C-order, 0 for solid
+long long labelCells(const VoxelGrid &g, std::vector<int32_t> &label)
+{
+    label.assign((size_t)g.cells(), 0);
+    long long n = 0;
+    for (long long k = 0; k < g.cells(); ++k)
+        if (g.v[k]) label[(size_t)k] = (int32_t)++n;
+    return n;
+}
+
+// one direction of the pull table for the x-range [x0, x1)
+void fillTableRow(const VoxelGrid &g, const std::vector<int32_t> &label, const int c[3], int32_t *row, int x0, int x1)
+{
+    for (int x = x0; x < x1; ++x)
+        for (int y = 0; y < g.ny; ++y)
+            for (int z = 0; z < g.nz; ++z) {
+                const int32_t me = label[(size_t)g.at(x, y, z)];
+                if (!me) continue;
+                const long long up = g.shifted(x, y, z, -c[0], -c[1], -c[2]);
+                const int32_t l = up >= 0 ? label[(size_t)up] : 0;
+                row[me - 1] = l ? l - 1 : -1;
+            }
+}
+} // namespace
+} // extern "C++"
+
+int chimp_voxel_table_host(int lattice, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask, int *n_own, int *n_pad,
+                           int32_t *table, int32_t *labels)
+{
+    VoxelGrid g;
+    if (voxelGrid(g, lattice, nx, ny, nz, voxels, periodic_mask)) return 1;
+    std::vector<int32_t> label;
+    const long long n = labelCells(g, label);
+    if (n == 0) return fail("the voxel array has no fluid cell");
+    const int nPad = (int)(((n + 31) / 32) * 32);
+    if (n_own) *n_own = (int)n;
+    if (n_pad) *n_pad = nPad;
+    if (labels) {
+        for (int i = 0; i < nPad; ++i) labels[i] = i < n ? i + 1 : 0;
+    }
+    if (table) {
+        const int nQ = latInfo(lattice).nQ;
+        for (int q = 0; q < nQ; ++q) {
+            int c[3];
+            lookupC(lattice, q, c);
+            int32_t *row = table + (size_t)q * nPad;
+            std::fill(row, row + nPad, -1);
+            parallelOverX(nx, [&](int x0, int x1) { fillTableRow(g, label, c, row, x0, x1); });
+        }
+    }
+    return 0;
+}
+
+int chimp_create_from_voxels(chimp_lattice **out, int lattice, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask,
+                             int n_fields, int index_form, int device)
+{
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    VoxelGrid g;
+    if (voxelGrid(g, lattice, nx, ny, nz, voxels, periodic_mask)) return 1;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return fail("no CUDA device available: this engine has no CPU fallback");
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    CUDA_OK(cudaSetDevice(device));
+    std::vector<int32_t> label;
+    const long long n = labelCells(g, label);
+    if (n == 0) return fail("the voxel array has no fluid cell");
+    const int nPad = (int)(((n + 31) / 32) * 32);
+    const int nQ = latInfo(lattice).nQ;
+    // one direction at a time: the host holds a single row of the table
+    int32_t *d_table = nullptr, *d_label = nullptr;
+    CUDA_OK(cudaMalloc(&d_table, (size_t)nQ * nPad * sizeof(int32_t)));
+    std::vector<int32_t> row((size_t)nPad);
+    int rc = 0;
+    for (int q = 0; q < nQ && !rc; ++q) {
+        int c[3];
+        lookupC(lattice, q, c);
+        std::fill(row.begin(), row.end(), -1);
+        parallelOverX(nx, [&](int x0, int x1) { fillTableRow(g, label, c, row.data(), x0, x1); });
+        if (cudaMemcpy(d_table + (size_t)q * nPad, row.data(), (size_t)nPad * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail("copy of the pull table to the device failed");
+    }
+    if (!rc) {
+        for (int i = 0; i < nPad; ++i) row[(size_t)i] = i < n ? i + 1 : 0;
+        if (cudaMalloc(&d_label, (size_t)nPad * sizeof(int32_t)) != cudaSuccess ||
+            cudaMemcpy(d_label, row.data(), (size_t)nPad * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail("copy of the label array to the device failed");
+    }
+    if (!rc) rc = chimp_create_from_device_table(out, lattice, (int)n, nPad, 0, d_table, d_label, n_fields, index_form, device);
+    cudaFree(d_table);
+    cudaFree(d_label);
+    return rc;
+}
+
+// Colour-gradient support tables of a two-field lattice from the same voxel array (twophase/main_TWOPHASE.cpp:280-284,
+// LButilities.h:12-22): phi slot of neighbor(q, n) -- own fluid node -> its slot, solid cell next to a fluid cell (the
+// reference's solid boundary nodes, LBgeometry.h:37-45; numbered in C-order) -> n_pad + k, anything else -> the zero
+// slot n_pad + n_extra -- and the constant colour wall_phi[cell] of those solid cells.
+int chimp_voxel_phi_table_host(int lattice, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask, const double *wall_phi,
+                               int *n_extra, int32_t *ptable, double *phi_extra)
+{
+    VoxelGrid g;
+    if (voxelGrid(g, lattice, nx, ny, nz, voxels, periodic_mask)) return 1;
+    const int nQ = latInfo(lattice).nQ;
+    std::vector<int32_t> label;
+    const long long n = labelCells(g, label);
+    if (n == 0) return fail("the voxel array has no fluid cell");
+    const int nPad = (int)(((n + 31) / 32) * 32);
+    // wall cells: solid with a fluid neighbour in any non-rest direction
+    std::vector<int32_t> wallNo((size_t)g.cells(), -1);
+    std::vector<uint8_t> isWall((size_t)g.cells(), 0);
+    parallelOverX(nx, [&](int x0, int x1) {
+        for (int x = x0; x < x1; ++x)
+            for (int y = 0; y < g.ny; ++y)
+                for (int z = 0; z < g.nz; ++z) {
+                    const long long k = g.at(x, y, z);
+                    if (g.v[k]) continue;
+                    for (int q = 0; q < nQ - 1; ++q) {
+                        int c[3];
+                        lookupC(lattice, q, c);
+                        const long long nb = g.shifted(x, y, z, c[0], c[1], c[2]);
+                        if (nb >= 0 && g.v[nb]) { isWall[(size_t)k] = 1; break; }
+                    }
+                }
+    });
+    int nWall = 0;
+    for (long long k = 0; k < g.cells(); ++k)
+        if (isWall[(size_t)k]) wallNo[(size_t)k] = nWall++;
+    if (n_extra) *n_extra = nWall;
+    if (phi_extra) {
+        if (!wall_phi) return fail("wall_phi is null");
+        for (long long k = 0; k < g.cells(); ++k)
+            if (isWall[(size_t)k]) phi_extra[wallNo[(size_t)k]] = wall_phi[k];
+    }
+    if (ptable) {
+        const int zeroSlot = nPad + nWall;
+        for (int q = 0; q < nQ; ++q) {
+            int c[3];
+            lookupC(lattice, q, c);
+            int32_t *row = ptable + (size_t)q * nPad;
+            std::fill(row, row + nPad, zeroSlot);
+            parallelOverX(nx, [&](int x0, int x1) {
+                for (int x = x0; x < x1; ++x)
+                    for (int y = 0; y < g.ny; ++y)
+                        for (int z = 0; z < g.nz; ++z) {
+                            const int32_t me = label[(size_t)g.at(x, y, z)];
+                            if (!me) continue;
+                            const long long nb = g.shifted(x, y, z, c[0], c[1], c[2]);
+                            if (nb < 0) continue;
+                            if (label[(size_t)nb]) row[me - 1] = label[(size_t)nb] - 1;
+                            else if (isWall[(size_t)nb]) row[me - 1] = nPad + wallNo[(size_t)nb];
+                        }
+            });
+        }
+    }
+    return 0;
+}
+
+int chimp_set_phi_table_from_voxels(chimp_lattice *c, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask, const double *wall_phi)
+{
+    if (check(c, true)) return 1;
+    if (c->nFields != 2) return fail("needs a two-field lattice");
+    int nExtra = 0;
+    if (chimp_voxel_phi_table_host(c->lattice, nx, ny, nz, voxels, periodic_mask, nullptr, &nExtra, nullptr, nullptr)) return 1;
+    std::vector<int32_t> ptable((size_t)c->li.nQ * c->nPad);
+    std::vector<double> extra((size_t)std::max(nExtra, 1), 0.0);
+    if (chimp_voxel_phi_table_host(c->lattice, nx, ny, nz, voxels, periodic_mask, wall_phi, &nExtra, ptable.data(), extra.data())) return 1;
+    CUDA_OK(cudaSetDevice(c->device));
+    int32_t *d_pt = nullptr;
+    double *d_ex = nullptr;
+    CUDA_OK(cudaMalloc(&d_pt, ptable.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&d_ex, extra.size() * sizeof(double)));
+    int rc = 0;
+    if (cudaMemcpy(d_pt, ptable.data(), ptable.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_ex, extra.data(), extra.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail("copy of the phi table to the device failed");
+    if (!rc) rc = chimp_set_phi_table_dev(c, d_pt, nExtra, d_ex);
+    cudaFree(d_pt);
+    cudaFree(d_ex);
+    return rc;
+}
+
 int chimp_num_own_nodes(chimp_lattice *c) { return c ? c->n : 0; }
 int chimp_host_table_info(chimp_lattice *c, long long *info6)
 {

@@ -89,6 +89,8 @@ int run(const std::string &inputFile, const std::string &prefix, int firstRank, 
                     }
                 }
             }
+            // the copies above ran on the legacy stream; the unpack kernels of step_end run on the engine's non-blocking streams
+            cudaDeviceSynchronize();
             for (auto &R : ranks) chimpCheck(chimp_step_end(R.gpu->handle()));
         }
     }

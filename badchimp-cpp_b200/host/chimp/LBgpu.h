@@ -3,6 +3,8 @@
 #ifndef CHIMP_LBGPU_H
 #define CHIMP_LBGPU_H
 
+#include <cstdint>
+
 #include "../../../include/chimp_b200.h"
 #include "LBbndmpi.h"
 #include "LBfield.h"
@@ -21,6 +23,32 @@ public:
     {
         chimpCheck(chimp_create(&h_, DXQY::chimpId, grid.size(), grid.neighborList().data(), int(bulkNodes.size()),
                                 bulkNodes.data(), nFields, device));
+    }
+    // straight from a raw voxel array [nx][ny][nz] (0 = solid), reference numbering, half-way bounce back at every solid
+    // link: the route to sizes the ASCII .vtklb loader cannot read (LBvtk.h:194-201).  Fields of such a lattice have
+    // numFluidNodes() + 1 rows (row 0 is the reference's dummy node).
+    GpuLattice(const std::vector<std::uint8_t> &voxels, int nx, int ny, int nz, int periodicMask, int nFields, int device = -1)
+    {
+        if (voxels.size() != std::size_t(nx) * ny * nz) chimp_host::die("voxel array does not hold nx*ny*nz cells");
+        chimpCheck(chimp_create_from_voxels(&h_, DXQY::chimpId, nx, ny, nz, voxels.data(), periodicMask, nFields, CHIMP_INDEX_COMPACT, device));
+        nNodes_ = chimp_num_own_nodes(h_) + 1;
+    }
+    int numFluidNodes() const { return chimp_num_own_nodes(h_); }
+    void initUniform(lbBase_t rho) { chimpCheck(chimp_init_uniform(h_, rho)); }
+    // two-field lattice from voxels: colour of the solid cells next to fluid (main_TWOPHASE.cpp:280-284)
+    void setWallColour(const std::vector<std::uint8_t> &voxels, int nx, int ny, int nz, int periodicMask, const std::vector<double> &wallPhi)
+    {
+        chimpCheck(chimp_set_phi_table_from_voxels(h_, nx, ny, nz, voxels.data(), periodicMask, wallPhi.data()));
+    }
+    double stepBGKTimed(lbBase_t tau, const std::valarray<lbBase_t> &bodyForce, int nSteps)
+    {
+        chimp_single_params p{};
+        p.collision = CHIMP_BGK;
+        p.tau = tau;
+        for (int d = 0; d < DXQY::nD; ++d) p.force[d] = bodyForce[d];
+        double ms = 0.0;
+        chimpCheck(chimp_step_timed(h_, &p, nSteps, &ms));
+        return ms;
     }
     ~GpuLattice() { chimp_destroy(h_); }
     GpuLattice(const GpuLattice &) = delete;

@@ -94,20 +94,27 @@ private:
                 if (pr != rankOf_[r] || !nrecv) continue;
                 const void *src = scalar ? chimp_scalar_send_buffer_dev(peer, j) : chimp_send_buffer_dev(peer, j);
                 void *dst = scalar ? chimp_scalar_recv_buffer_dev(me, k) : chimp_recv_buffer_dev(me, k);
-                // population counts reported by chimp_neighbor_info already cover all LbFields
-                if (cudaMemcpy(dst, src, std::size_t(nrecv) * sizeof(double), cudaMemcpyDeviceToDevice) != cudaSuccess) rc = 1;
+                // population counts reported by chimp_neighbor_info already cover all LbFields.  The copy goes onto the
+                // stream the engine handed over: the unpack kernels it enqueues there afterwards are ordered behind it (the
+                // engine's streams are non-blocking, so a copy on the legacy default stream would not be)
+                if (cudaMemcpyAsync(dst, src, std::size_t(nrecv) * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) rc = 1;
             }
         }
-        barrier(); // nobody overwrites a send buffer before its reader is done
+        // my copies have read the peers' send buffers completely before anybody may overwrite them
+        if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = 1;
+        barrier();
         return rc;
     }
     int allreduce(int r, void *dev, int count, void *stream)
     {
-        if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return 1;
+        // everything on the engine's stream: the kernels that consume the sum are enqueued there after this call returns
+        cudaStream_t s = (cudaStream_t)stream;
         std::vector<double> mine(count);
-        if (cudaMemcpy(mine.data(), dev, std::size_t(count) * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+        if (cudaMemcpyAsync(mine.data(), dev, std::size_t(count) * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
         allreduceHost(r, mine.data(), count);
-        return cudaMemcpy(dev, mine.data(), std::size_t(count) * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess;
+        if (cudaMemcpyAsync(dev, mine.data(), std::size_t(count) * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+        return cudaStreamSynchronize(s) != cudaSuccess; // `mine` leaves scope: the copy must have read it
     }
     static int exchangeCb(void *u, void *s) { auto *c = (Ctx *)u; return c->self->exchange(c->r, s, false); }
     static int scalarCb(void *u, void *s) { auto *c = (Ctx *)u; return c->self->exchange(c->r, s, true); }

@@ -91,6 +91,23 @@ int chimp_create_from_device_table(chimp_lattice **out, int lattice, int n_bulk,
                                    const int32_t *table_dev, const int32_t *label_dev, int n_fields,
                                    int index_form, int device);
 
+/* Structured geometry ingest for HOST code (C / C++ mains without torch): one rank's lattice straight from a raw
+ * voxel array -- replaces vtklb.py -> ASCII file -> LBvtk (LBvtk.h:221-262), whose int offsets stop at 2 GiB of text
+ * (LBvtk.h:194-201), so a main reaches 512^3 and beyond.  voxels is uint8 [nx][ny][nz] in C-order (a 2-D lattice takes
+ * [nx][ny], nz = 1), 0 = solid; periodic_mask bit 0/1/2 = x/y/z periodic, other axes are closed.  Own fluid nodes
+ * get the reference's labels 1..N in C-order (vtklb.py:92-94), so chimp_upload_lbfield / chimp_download_* work on
+ * arrays of N + 1 rows; std_case semantics: half-way bounce back on every link into a solid (LBhalfwaybb.h:37-63).
+ * chimp_voxel_table_host is the host half alone (no CUDA call): sizes, and -- when the pointers are not NULL -- the
+ * pull table int32 [nQ][n_pad] and labels [n_pad].  chimp_set_phi_table_from_voxels adds the colour-gradient tables
+ * of a two-field lattice (wall colour wall_phi[cell] at the solid cells next to fluid, main_TWOPHASE.cpp:280-284). */
+int chimp_voxel_table_host(int lattice, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask, int *n_own, int *n_pad,
+                           int32_t *table, int32_t *labels);
+int chimp_create_from_voxels(chimp_lattice **out, int lattice, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask,
+                             int n_fields, int index_form, int device);
+int chimp_voxel_phi_table_host(int lattice, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask, const double *wall_phi,
+                               int *n_extra, int32_t *ptable, double *phi_extra);
+int chimp_set_phi_table_from_voxels(chimp_lattice *, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask, const double *wall_phi);
+
 void chimp_destroy(chimp_lattice *);
 
 /* ---- state transfer in reference layout and labels.

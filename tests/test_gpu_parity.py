@@ -39,6 +39,8 @@ class InProcessRanks:
                     assert other.neighbor_info(ko)[1] == nrecv
                     if nrecv:
                         assert self.rt.cudaMemcpy(lat.recv_buffer_ptr(k), other.send_buffer_ptr(ko), nrecv * 8, 3) == 0
+            # device-to-device copies on the legacy stream do not order against the engine's non-blocking streams
+            assert self.rt.cudaDeviceSynchronize() == 0
             for lat in self.lats:
                 lat.step_end()
             for lat in self.lats:
@@ -285,6 +287,9 @@ class ThreadedRanks:
                     src, dst = other.send_buffer_ptr(ko), lat.recv_buffer_ptr(k)
                 if cnt:
                     assert self.rt.cudaMemcpy(dst, src, cnt * 8, 3) == 0
+            # the copies ran on the legacy stream, the unpack kernels follow on the engine's non-blocking stream: the
+            # data must have landed (and the peers' send buffers been read) before anybody goes on
+            assert self.rt.cudaDeviceSynchronize() == 0
             self.barrier.wait()
         return cb
 
@@ -300,6 +305,7 @@ class ThreadedRanks:
                 total = total + self.shared[k]
             self.barrier.wait()
             assert self.rt.cudaMemcpy(dev, total.ctypes.data_as(C.c_void_p), count * 8, 1) == 0
+            assert self.rt.cudaDeviceSynchronize() == 0
         return cb
 
     def run(self, fn):
