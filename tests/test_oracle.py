@@ -61,7 +61,7 @@ def run_port_case(g, upto):
     return tabs, ranks
 
 
-@pytest.mark.parametrize("name", [n for n in helpers.all_golden_names() if not n.startswith("forcing_")])
+@pytest.mark.parametrize("name", helpers.all_golden_names())
 def test_port_reproduces_reference_dumps(name):
     g = helpers.Golden(name)
     nf = 2 if g.case == "twophase" else 1
