@@ -8,6 +8,7 @@
 #include "LBgrid.h"
 #include "LBhalfwaybb.h"
 #include "LBbndmpi.h"
+#include "LBcollision.h"
 #include "LBgpu.h"
 #include "LBranks.h"
 #include "Input.h"

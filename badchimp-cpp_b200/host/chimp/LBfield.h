@@ -106,6 +106,12 @@ public:
         return data_[std::slice(std::size_t(nFields_ * DXQY::nQ) * nodeNo + DXQY::nQ * fieldNo, DXQY::nQ, 1)];
     }
     void swapData(LbField &other) { data_.swap(other.data_); }
+    // push streaming of one node: f(fieldNo, q, neighbor(q, nodeNo)) = fNew[q] for all q, rest direction included
+    template <typename GRID, typename T>
+    void propagateTo(int fieldNo, int nodeNo, const T &fNew, const GRID &grid)
+    {
+        for (int q = 0; q < DXQY::nQ; ++q) (*this)(fieldNo, q, grid.neighbor(q, nodeNo)) = fNew[q];
+    }
     int num_fields() const { return nFields_; }
     int getNumNodes() const { return nNodes_; }
     lbBase_t *data() { return &data_[0]; }

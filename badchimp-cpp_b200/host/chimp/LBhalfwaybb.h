@@ -2,10 +2,12 @@
 // LBhalfwayhelperclass.h:110-253): per boundary node the direction pairs are classed beta (one side
 // solid; the stored direction is the unknown one, pointing away from the wall), gamma (both fluid)
 // or delta (both solid).  The copies the reference's apply() performs after streaming are folded
-// into the engine's pull table: hand the object to GpuLattice::add().
+// into the engine's pull table: hand the object to GpuLattice::add().  apply() itself is kept for host
+// loops (checks, small cases): it performs the same copies on a host LbField after swapData.
 #ifndef CHIMP_LBHALFWAYBB_H
 #define CHIMP_LBHALFWAYBB_H
 
+#include "LBfield.h"
 #include "LBgrid.h"
 
 template <typename DXQY>
@@ -34,6 +36,27 @@ public:
             for (int q : gamma) *l++ = q;
             for (int q : delta) *l++ = q;
         }
+    }
+    // half-way bounce back of one field after streaming: the unknown direction of a beta link takes the value that
+    // left the node towards the wall; both directions of a delta link do
+    void apply(int fieldNo, LbField<DXQY> &f, const Grid<DXQY> &grid) const
+    {
+        for (int b = 0; b < size(); ++b) {
+            const int node = nodes_[b];
+            for (int q : beta(b)) {
+                const int r = dirRev(q);
+                f(fieldNo, q, node) = f(fieldNo, r, grid.neighbor(r, node));
+            }
+            for (int q : delta(b)) {
+                const int r = dirRev(q);
+                f(fieldNo, q, node) = f(fieldNo, r, grid.neighbor(r, node));
+                f(fieldNo, r, node) = f(fieldNo, q, grid.neighbor(q, node));
+            }
+        }
+    }
+    void apply(LbField<DXQY> &f, const Grid<DXQY> &grid) const
+    {
+        for (int n = 0; n < f.num_fields(); ++n) apply(n, f, grid);
     }
     int size() const { return int(nodes_.size()); }
     int nodeNo(int b) const { return nodes_[b]; }

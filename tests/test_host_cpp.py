@@ -245,3 +245,84 @@ def test_std_case_app_writes_reference_vtk_files(tmp_path):
                     % (step, step, g.args["tau"], F[0], F[1], F[2]))
     subprocess.run([exe, g.lattice, str(deck), prefix, "0", str(tmp_path / "out.bin"), str(g.nranks), str(tmp_path / "vtk")], check=True)
     assert compare_vtk_tree(os.path.join(helpers.GOLDEN, g.name + ".vtk"), str(tmp_path / "vtk")) == 3
+
+
+def _read_cpu_loop(path, n_fields, nq, nd):
+    data = open(path, "rb").read()
+    (sz,) = struct.unpack_from("<i", data, 0)
+    p = 4
+    f = np.frombuffer(data, dtype="<f8", count=sz * n_fields * nq, offset=p).reshape(sz, n_fields, nq)
+    p += 8 * sz * n_fields * nq
+    rho = np.frombuffer(data, dtype="<f8", count=sz * n_fields, offset=p).reshape(sz, n_fields)
+    p += 8 * sz * n_fields
+    vel = np.frombuffer(data, dtype="<f8", count=sz * nd, offset=p).reshape(sz, nd)
+    return f, rho, vel
+
+
+@pytest.mark.parametrize("name", ["std_d3q19_p1", "trt_d3q19_p1", "std_d2q9_channel", "twophase_d3q19_p1", "twophase_d2q9_p1"])
+def test_host_mirror_per_node_functions_reproduce_the_reference(name, tmp_path):
+    """calcRho / calcVel / calcOmegaBGK[TRT] / calcDeltaOmegaF[TRT] / calcDeltaOmegaST / calcDeltaOmegaRC / grad /
+    vecNorm / initiateLbField / propagateTo / swapData / HalfWayBounceBack::apply of the host mirror
+    (host/chimp/LBcollision.h, LBfield.h, LBhalfwaybb.h), driven by the reference's loop bodies in
+    host/apps/cpu_loop.cpp on the CPU: populations, rho and u equal the reference's own dumps bit for bit"""
+    exe = os.path.join(HOST, "apps", "cpu_loop")
+    src = exe + ".cpp"
+    deps = [src] + [os.path.join(HOST, "chimp", f) for f in os.listdir(os.path.join(HOST, "chimp"))]
+    if not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-o", exe, src], check=True)
+    g = helpers.Golden(name)
+    lg, tabs = helpers.build_tables(g)
+    t = tabs[0]
+    attrs = {k[5:]: g.z[k] for k in g.z.files if k.startswith("attr.")}
+    t.write_vtklb(str(tmp_path / "tmp0.vtklb"), attrs)
+    step = max(g.dump)
+    a = g.args
+    F = g.force()[: lg.nd]
+    out = str(tmp_path / "out.bin")
+    if g.case == "twophase":
+        kind, nf = "twophase", 2
+        params = [repr(a["tau2"][0]), repr(a["tau2"][1]), repr(a["sigma"]), repr(a["beta"]), repr(a["momx"])] + [repr(x) for x in F[1:]]
+    elif "trt" in a:
+        kind, nf = "trt", 1
+        params = [repr(a["trt"][0]), repr(a["trt"][1])] + [repr(x) for x in F]
+    else:
+        kind, nf = "std", 1
+        params = [repr(a.get("tau", 0.8))] + [repr(x) for x in F]
+    subprocess.run([exe, kind, g.lattice, str(tmp_path / "tmp"), out, str(step)] + params, check=True, capture_output=True)
+    f, rho, vel = _read_cpu_loop(out, nf, lg.nq, lg.nd)
+    bulk = t.bulk_nodes()
+    assert np.array_equal(f[bulk], g.f(0, step, nf)[bulk])
+    assert np.array_equal(rho[bulk], g.rec(0, "step%d.rho" % step).reshape(-1, nf)[bulk])
+    assert np.array_equal(vel[bulk], g.rec(0, "step%d.vel" % step).reshape(-1, lg.nd)[bulk])
+
+
+@pytest.mark.parametrize("lattice", ["D2Q9", "D3Q19"])
+def test_host_mirror_mass_source_terms_and_equilibrium(lattice, tmp_path):
+    """calcDeltaOmegaQ / calcDeltaOmegaQTRT (LBcollision.h:79-121) and calcfeq (LButilities.h:74-91) of the host mirror
+    against the same expressions evaluated term by term in IEEE doubles"""
+    exe = os.path.join(HOST, "apps", "cpu_loop")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-o", exe, exe + ".cpp"], check=True)
+    pkg = helpers.load_package()
+    basis = pkg.geometry.BASIS[lattice]
+    w = pkg.cases.lattice_weights(lattice)
+    tau, ts, ta, src, rho = 0.83, 0.77, 1.19, 3.1e-4, 1.0123
+    u = [0.0123, -0.0231, 0.0072][: basis.shape[1]]
+    r = subprocess.run([exe, "unitq", lattice, repr(tau), repr(ts), repr(ta), repr(src), repr(rho)] + [repr(x) for x in u],
+                       capture_output=True, text=True, check=True)
+    got = np.array([[float(x) for x in line.split()] for line in r.stdout.strip().splitlines()])
+    u2 = u[0] * u[0] + u[1] * u[1]
+    if len(u) == 3:
+        u2 = u2 + u[2] * u[2]
+    c2 = 1.0 / 3.0
+    for q in range(len(basis)):
+        cu, first = 0.0, True
+        for d in range(len(u)):
+            c = int(basis[q, d])
+            if c:
+                term = u[d] if c > 0 else -u[d]
+                cu = term if first else cu + term
+                first = False
+        e = (1.0 + 3.0 * cu + 4.5 * (cu * cu - c2 * u2))
+        assert got[q, 0] == (1 - 0.5 / tau) * src * w[q] * e
+        assert got[q, 1] == src * w[q] * ((1 - 0.5 / ta) * 3.0 * cu + (1 - 0.5 / ts) * (1.0 + 4.5 * (cu * cu - c2 * u2)))
+        assert got[q, 2] == rho * w[q] * e

@@ -161,3 +161,32 @@ def test_port_equals_the_reference_on_random_cases(seed, tmp_path):
         assert np.array_equal(pr.rho[bulk, 0], rec["step%d.rho" % steps][bulk])
     assert np.array_equal(pr.f[bulk], ref_f[bulk]), (kind, lattice, shape, periodic)
     assert np.array_equal(pr.vel[bulk], rec["step%d.vel" % steps].reshape(t.size, -1)[bulk])
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="needs oracle/_ref/ref_driver (the reference's own headers)")
+def test_port_equals_the_reference_at_config0_size(tmp_path):
+    """BASELINE configs[0] -- std_case, D3Q19 BGK, 128^3 sphere pack, 1 rank -- through the reference's own headers and
+    through the port: populations, rho, u of all 738 k fluid nodes bit for bit after 3 steps (the same geometry files
+    and command line as the gpu-marked 128^3 test, tests/test_gpu_scale_parity.py)"""
+    sys.path.insert(0, os.path.join(helpers.ROOT, "oracle"))
+    from recfile import read_rec
+    port = helpers.oracle_port()
+    pkg = helpers.load_package()
+    G = pkg.geometry
+    size, steps, tau, force = 128, 3, 0.8, (1e-6, 0.0, 0.0)
+    geo = G.sphere_pack((size,) * 3, size / 8.0, 0.35, 1234).astype(int)
+    t = G.LatticeGeometry(geo, "D3Q19", "xyz").all_ranks()[0]
+    ones = np.ones(geo.shape)
+    t.write_vtklb(str(tmp_path / "tmp0.vtklb"), {"init_rho": ones})
+    subprocess.run([REF_DRIVER, "--case", "std_case", "--lattice", "D3Q19", "--dir", str(tmp_path), "--out", str(tmp_path), "--nranks", "1",
+                    "--steps", str(steps), "--dump", str(steps), "--no-tables", "--tau", repr(tau), "--force", ",".join(repr(x) for x in force)],
+                   check=True, capture_output=True)
+    rec = read_rec(str(tmp_path / "rank0.rec"))
+    bulk = t.bulk_nodes()
+    assert len(bulk) == 738492
+    pr = port.PortRank(1, t.neigh, bulk, 1, t.halfway_bb(t.fluid_bnd_nodes()))
+    pr.f[:] = pkg.cases.std_case_initial_state(t, ones)[0]
+    pr.step_std_case(steps, tau=tau, force=force)
+    assert np.array_equal(pr.f[bulk, 0], rec["step%d.f" % steps].reshape(-1, 19)[bulk])
+    assert np.array_equal(pr.rho[bulk, 0], rec["step%d.rho" % steps][bulk])
+    assert np.array_equal(pr.vel[bulk], rec["step%d.vel" % steps].reshape(-1, 3)[bulk])
