@@ -421,6 +421,41 @@ def _e2e_cycle(pkg, rl, wl, run, steps, total, barrier):
             "cycle": "per rank: upload LbField (pinned host, reference AoS) + %d steps + download rho, vel; wall clock, max over ranks; one untimed cycle before" % steps}
 
 
+def _e2e_from_init_rho(pkg, rl, wl, run, steps, device):
+    """Secondary end-to-end figure (one GPU, single-field workloads): the data flow of the reference main itself -- the
+    host holds the ScalarField init_rho (std_case/main.cpp:62-69), the populations are formed from it on the device
+    (f = w_q rho, :92-96 / initiateLbField), K steps, rho and vel come back for output (:149-151).  Only 8 bytes per node
+    cross the bus on the way in, instead of the whole LbField of the primary e2e cycle.  Rank-local, no collectives."""
+    import torch
+    capi = pkg.capi
+    lib = capi.lib()
+    lat = rl.lat
+    n, nd = rl.n, lat.nd
+    host_init = torch.ones((n + 1,), dtype=torch.float64, pin_memory=True)     # rows by reference label, row 0 = dummy node
+    host_rho = torch.empty((n + 1, 1), dtype=torch.float64, pin_memory=True)
+    host_vel = torch.empty((n + 1, nd), dtype=torch.float64, pin_memory=True)
+    dev_rho = torch.empty((n,), dtype=torch.float64, device=device)
+
+    def cycle(k):
+        # single-rank ingest lattices keep the reference's label order on the device: slot = label - 1
+        dev_rho.copy_(host_init[1:], non_blocking=True)
+        torch.cuda.synchronize()
+        lat.init_equilibrium_dev(dev_rho.data_ptr())
+        run.step(k)
+        capi._check(lib.chimp_download_rho(lat.h, C.c_void_p(host_rho.data_ptr()), C.c_int(1)))
+        capi._check(lib.chimp_download_vel(lat.h, C.c_void_p(host_vel.data_ptr())))
+
+    cycle(1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cycle(steps)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": host_init.numel() * 8 / steps,
+            "d2h_bytes_per_step": (host_rho.numel() + host_vel.numel()) * 8 / steps,
+            "mean_rho_error": abs(float(host_rho[1:].mean()) - 1.0),
+            "cycle": "upload init_rho (pinned host ScalarField) + f = w_q rho on the device + %d steps + download rho, vel; wall clock; one untimed cycle before" % steps}
+
+
 def _measure(pkg, rl, wl, args, total, barrier, rank, sample_clocks):
     """warm-up, K timed steps (CUDA events on the engine's stream, max over ranks), clocks under load"""
     import torch
@@ -524,6 +559,12 @@ def run_b200(args):
         per_rank = pr.cpu().numpy()
     # no try/except here: an exception caught on one rank only would leave the others waiting in a collective
     e2e = _e2e_cycle(pkg, rl, wl, m["run"], args.steps, total, barrier)
+    e2e_rho = None
+    if world == 1 and wl["physics"] in ("single", "one_phase"):
+        try:    # rank-local and secondary: a failure here must not cost the line
+            e2e_rho = _e2e_from_init_rho(pkg, rl, wl, m["run"], args.steps, device)
+        except Exception as exc:  # pragma: no cover
+            e2e_rho = {"value": None, "unit": "MLUPS", "error": str(exc)}
     irregular, index_bytes = rl.lat.irregular_fraction(), rl.lat.index_bytes_per_node()
     halo_bytes, halo_mode = rl.halo_bytes, rl.halo_mode
     rl.lat.close()
@@ -583,6 +624,8 @@ def run_b200(args):
                              "algorithmic_gb_per_launch": b_alg * n_total / world / 1e9, "peak_source": peak_src, "bytes_per_node": b_alg,
                              "per": "GPU (mean)" if world > 1 else "GPU", "frac_of_nominal_8TBs": achieved / 8000.0},
                 "e2e": e2e, "gpu_launches": m["launches"], "clocks": _summarize_clocks(m["samples"]), "parity": parity}
+        if e2e_rho:
+            line["e2e_from_init_rho"] = e2e_rho
         if weak:
             line["weak"] = weak
         if world == 1 and not args.no_cpu_baseline:

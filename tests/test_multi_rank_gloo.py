@@ -163,3 +163,42 @@ def test_twophase_scalar_ring_and_balanced_cuts_over_gloo(world):
     cuts, counts = res[0][2], res[0][3]
     assert cuts[0] == 0 and cuts[-1] == 6 * world and all(b > a for a, b in zip(cuts, cuts[1:]))
     assert max(counts) - min(counts) <= 2 * 9 * 8                              # within one z-layer of each other
+
+
+def _strong_split_worker(rank, world, port, nz, out_q):
+    """the cut planes bench.py --gpus N uses for the strong-scaling split (workloads._balanced_range), slabs of unequal
+    thickness included (nz not divisible by the rank count)"""
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests"))
+    pkg = helpers.load_package()
+    ing = importlib.import_module("badchimp_cpp_b200.ingest")
+    multi = importlib.import_module("badchimp_cpp_b200.multi")
+    W = importlib.import_module("badchimp_cpp_b200.workloads")
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        wl = dict(W.WORKLOADS["std_case"])
+        gshape = (16, 16, nz)
+        cuts = W._balanced_range(multi, wl, ing, gshape, rank, world, torch.device("cpu"), True)
+        full = ing.sphere_pack_slab(gshape, gshape[0] / 8.0, W.PACK_POROSITY, W.PACK_SEED, 0, nz)
+        counts = [int(full[:, :, cuts[k]:cuts[k + 1]].sum()) for k in range(world)]
+        layer_max = int(full.reshape(-1, nz).sum(axis=0).max())
+        out_q.put((rank, [int(c) for c in cuts], counts, layer_max))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nz", [(2, 16), (3, 16), (3, 13)])
+def test_strong_scaling_cut_planes_over_gloo(world, nz):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_strong_split_worker, args=(r, world, port, nz, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cuts, counts, layer_max = res[0][1], res[0][2], res[0][3]
+    assert all(r[1] == cuts for r in res)                                       # every rank computes the same planes
+    assert cuts[0] == 0 and cuts[-1] == nz and all(b > a for a, b in zip(cuts, cuts[1:]))
+    assert max(counts) - min(counts) <= 2 * layer_max                           # within a z-layer or so of each other
