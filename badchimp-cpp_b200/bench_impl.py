@@ -496,6 +496,84 @@ def _measure(pkg, rl, wl, args, total, barrier, rank, sample_clocks):
     return dict(ms=ms, ms_max=ms_max, launches=int(l2 - l1), samples=samples, mass_err=mass_err, run=run)
 
 
+def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, peak):
+    """One GPU, default workload only: the other BASELINE.json configurations timed in the same run (secondary numbers
+    under "other_workloads": same K / W, CUDA events on the engine's stream, state larger than L2), each with its own
+    parity probe against the oracle port.  Everything here is rank-local and guarded: a failure costs that entry only.
+    The main lattice is reused for the TRT collision (same geometry) and closed afterwards."""
+    import torch
+    out = []
+    t_begin = time.perf_counter()
+
+    def timed_entry(name, rl, wl, extra=None):
+        run = _Runner(rl, wl)
+        run.step(max(args.warmup, 3))
+        rl.lat.synchronize()
+        ms = run.timed(args.steps)
+        rl.lat.synchronize()
+        n = rl.n
+        achieved = wl["b_alg"] * n / (ms / args.steps * 1e-3) / 1e9
+        e = {"workload_key": name, "workload": W.describe(wl, args.size or wl["size"]), "fluid_nodes": n, "steps": args.steps,
+             "ms_per_step": ms / args.steps, "value": n * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS",
+             "roofline": {"bytes_per_node": wl["b_alg"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
+             "index_bytes_per_node": rl.lat.index_bytes_per_node(), "irregular_tile_fraction": rl.lat.irregular_fraction()}
+        if extra:
+            e.update(extra)
+        return e
+
+    def guarded(name, fn):
+        if time.perf_counter() - t_begin > 150.0:
+            out.append({"workload_key": name, "skipped": "time budget of the default run used up"})
+            return
+        try:
+            out.append(fn())
+        except Exception as exc:  # pragma: no cover
+            out.append({"workload_key": name, "error": str(exc)[:300]})
+        try:
+            torch.cuda.empty_cache()
+        except Exception:  # pragma: no cover
+            pass
+
+    def probe(name, wl, interior=False):
+        try:
+            return parity_probe(pkg, ingest, multi, wl, name, 0, 1, device, index_form, args.halo, interior)
+        except BaseException as exc:  # a failed probe is reported, not fatal, for a secondary entry
+            return {"error": str(exc)[:300]}
+
+    # TRT on the lattice of the main run
+    def trt():
+        wl = W.WORKLOADS["trt"]
+        main_rl.lat.init_uniform(1.0)
+        return timed_entry("trt", main_rl, wl, {"parity": probe("trt", wl)})
+    guarded("trt", trt)
+    try:
+        main_rl.lat.close()
+        torch.cuda.empty_cache()
+    except Exception:  # pragma: no cover
+        pass
+
+    def fresh(name, interior=False):
+        def fn():
+            wl = W.WORKLOADS[name]
+            par = probe(name, wl, interior)
+            rl = W.build(pkg, ingest, multi, wl, wl["size"], 0, 1, device, "strong", index_form, interior_domains=interior)
+            try:
+                e = timed_entry(name + ("+interior_domains" if interior else ""), rl, wl, {"parity": par})
+                rho, _ = rl.lat.download_moments_device_order()
+                if rl.lat.n_fields == 1:
+                    e["mean_rho_error"] = abs(float(rho.mean()) - 1.0)
+            finally:
+                rl.lat.close()
+            return e
+        return fn
+    guarded("one_phase", fresh("one_phase"))
+    guarded("one_phase+interior_domains", fresh("one_phase", True))
+    guarded("twophase", fresh("twophase"))
+    guarded("d2q9_channel", fresh("d2q9_channel"))
+    guarded("d3q27_dense", fresh("d3q27_dense"))
+    return out
+
+
 def run_b200(args):
     import importlib
     import torch
@@ -567,7 +645,14 @@ def run_b200(args):
             e2e_rho = {"value": None, "unit": "MLUPS", "error": str(exc)}
     irregular, index_bytes = rl.lat.irregular_fraction(), rl.lat.index_bytes_per_node()
     halo_bytes, halo_mode = rl.halo_bytes, rl.halo_mode
-    rl.lat.close()
+    others = None
+    if world == 1 and args.workload == "std_case" and not args.size and not args.no_extra_workloads:
+        try:
+            others = _extra_workloads(pkg, ingest, multi, W, rl, args, device, index_form, _peaks()[0])   # closes rl.lat
+        except Exception as exc:  # pragma: no cover -- secondary numbers must never cost the line
+            others = [{"error": str(exc)[:300]}]
+    else:
+        rl.lat.close()
     del rl
     torch.cuda.empty_cache()
 
@@ -626,6 +711,8 @@ def run_b200(args):
                 "e2e": e2e, "gpu_launches": m["launches"], "clocks": _summarize_clocks(m["samples"]), "parity": parity}
         if e2e_rho:
             line["e2e_from_init_rho"] = e2e_rho
+        if others:
+            line["other_workloads"] = others
         if weak:
             line["weak"] = weak
         if world == 1 and not args.no_cpu_baseline:

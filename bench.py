@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N>1: split one lattice (strong) or one block per GPU (weak); default per workload")
     ap.add_argument("--interior-domains", action="store_true", help="one_phase: two interior domains with mass sources (per-step mass-change sum)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity probe against the oracle port before timing")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="N=1, default workload: do not time the other BASELINE configurations in the same run")
     ap.add_argument("--no-weak", action="store_true", help="N>1: skip the secondary weak-scaling measurement")
     ap.add_argument("--no-traffic", action="store_true", help="N=1: skip the ncu child run that measures DRAM traffic of one step")
     ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
