@@ -24,11 +24,9 @@
 
 #include "../../include/chimp_b200.h"
 #include "kernels.cuh"
-#include "twophase_fused.cuh"
 
 namespace chimp {
 __global__ void fillKernel(double *p, double v, long long count);
-__global__ void tilePhiRangesKernel(const int32_t *, int, int, int, int, int4 *);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *, int, long long);
 __global__ void kernelTableKernel(const int32_t *, int32_t *, int, int, int, int, long long);
@@ -185,7 +183,7 @@ struct chimp_lattice {
     unsigned long long *d_trace = nullptr;           // CHIMP_TRACE: per-step device timestamps [traceCap][4]
     unsigned long long *traceCursor = nullptr;
     int traceCap = 0;
-    bool trace = false, tpFusedEnv = false, peerFusedEnv = true;
+    bool trace = false, peerFusedEnv = true;
     std::string peerWhy;
     // two-phase over peer memory: sum mailbox of every rank (world pointers on the device), my rank / world size
     MailSlot *d_mail = nullptr;
@@ -195,15 +193,6 @@ struct chimp_lattice {
     chimp_allreduce_fn allreduce = nullptr;
     void *allreduceUser = nullptr;
     std::vector<std::vector<long long>> hPhiSendSrc, hPhiRecvDst;
-    // fused two-phase step (twophase_fused.cuh): item order, per-tile dependencies, completion counters
-    int32_t *d_tpSeq = nullptr;
-    int4 *d_tpDeps = nullptr;
-    unsigned *d_tpDone = nullptr, *d_tpTicket = nullptr;
-    double *d_tpMom = nullptr;
-    int tpTiles = 0;
-    unsigned tpLaunchNo = 0;
-    bool tpReady = false, tpMomValid = false;
-    int forceNext = 0, forceLast = 0; // d_forceX holds two values: the one the next step uses / the last step used
     int32_t *d_slotOf = nullptr; // reference label -> device slot (-1: not an own node), built on first use
     long long steps = 0;
 };
@@ -243,7 +232,6 @@ int allocateState(chimp_lattice *c)
         return v ? atoll(v) : dflt;
     };
     c->trace = envInt("CHIMP_TRACE", 0) == 1;
-    c->tpFusedEnv = envInt("CHIMP_TP_FUSED", 0) == 1;
     c->peerFusedEnv = envInt("CHIMP_PEER_FUSED", 1) != 0;
     c->timeoutNs = (unsigned long long)std::max(1ll, envInt("CHIMP_PEER_TIMEOUT_MS", 20000)) * 1000000ull;
     return 0;
@@ -890,7 +878,6 @@ void chimp_destroy(chimp_lattice *c)
     freeDev(c->d_sendMask); freeDev(c->d_sendDst); freeDev(c->d_extraStart); freeDev(c->d_extra);
     freeDev(c->d_peerCounter); freeDev(c->d_trace);
     if (c->h_error) cudaFreeHost(c->h_error);
-    freeDev(c->d_tpSeq); freeDev(c->d_tpDeps); freeDev(c->d_tpDone); freeDev(c->d_tpTicket); freeDev(c->d_tpMom);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
@@ -957,7 +944,6 @@ static int acquireStaging(chimp_lattice *c, size_t bytes, Staging &st)
 int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
 {
     if (check(c, true)) return 1;
-    c->tpMomValid = false;
     if (c->nNodes <= 0) return fail("upload in reference layout needs a lattice created from reference tables");
     CUDA_OK(cudaSetDevice(c->device));
     if (labelRange(c)) return 1;
@@ -1359,7 +1345,6 @@ int chimp_step_timed(chimp_lattice *c, const chimp_single_params *p, int n_steps
 int chimp_init_uniform(chimp_lattice *c, double rho)
 {
     if (check(c, true)) return 1;
-    c->tpMomValid = false;
     CUDA_OK(cudaSetDevice(c->device));
     std::vector<double> wq(c->li.nQ);
     for (int q = 0; q < c->li.nQ; ++q) wq[q] = chimp_lattice_w(c->lattice, q) * rho;
@@ -1377,7 +1362,6 @@ int chimp_init_uniform(chimp_lattice *c, double rho)
 int chimp_init_equilibrium_dev(chimp_lattice *c, const double *rho_dev)
 {
     if (check(c, true)) return 1;
-    c->tpMomValid = false;
     if (!rho_dev) return fail("rho_dev is null");
     CUDA_OK(cudaSetDevice(c->device));
     CUDA_OK(cudaDeviceSynchronize()); // rho may come from another stream
@@ -1397,7 +1381,6 @@ int chimp_init_equilibrium_dev(chimp_lattice *c, const double *rho_dev)
 int chimp_set_phi_table_dev(chimp_lattice *c, const int32_t *ptable_dev, int n_extra, const double *phi_extra_dev)
 {
     if (check(c, true)) return 1;
-    c->tpReady = false;
     if (c->nFields != 2) return fail("needs a two-field lattice");
     if (!ptable_dev || n_extra < 0 || (n_extra > 0 && !phi_extra_dev)) return fail("bad phi table arguments");
     CUDA_OK(cudaSetDevice(c->device));
@@ -1498,133 +1481,6 @@ void twoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom, cudaStre
 } // namespace
 } // extern "C++"
 
-extern "C++" {
-namespace {
-// item order and dependencies of the fused two-phase step (see twophase_fused.cuh)
-int setupFused(chimp_lattice *c)
-{
-    const int nTiles = (c->n + CHIMP_FUSED_TILE - 1) / CHIMP_FUSED_TILE;
-    const int nChunks = ((nTiles - 1) >> CHIMP_FUSED_CHUNK_SHIFT) + 1;
-    int4 *d_ranges = nullptr;
-    CUDA_OK(cudaMalloc(&d_ranges, (size_t)nTiles * sizeof(int4)));
-    const int window = std::max(c->n / 4, 1);
-    tilePhiRangesKernel<<<nTiles, CHIMP_FUSED_TILE, 0, c->stream>>>(c->d_ptable, c->n, c->nPad, c->li.nQ, window, d_ranges);
-    ++g_launches;
-    std::vector<int4> ranges(nTiles);
-    cudaError_t e = cudaMemcpyAsync(ranges.data(), d_ranges, (size_t)nTiles * sizeof(int4), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_ranges);
-    if (e != cudaSuccess) return fail("tile range kernel failed: %s", cudaGetErrorString(e));
-    // A runs ahead of D by the reach of the stencil plus `lead` tiles (about one wave of resident blocks), so
-    // that a D item normally finds its dependencies complete; periodic images at the far end come first
-    int lead = 320;
-    if (const char *env = getenv("CHIMP_TP_LEAD")) lead = std::max(0, atoi(env));
-    std::vector<int32_t> seq;
-    seq.reserve(2 * (size_t)nTiles);
-    std::vector<char> emitted(nTiles, 0);
-    std::vector<int4> deps(nTiles);
-    int aNext = 0;
-    auto emitA = [&](int lo, int hi) {
-        for (int t = lo; t <= hi; ++t)
-            if (!emitted[t]) { emitted[t] = 1; seq.push_back(t); }
-    };
-    for (int t = 0; t < nTiles; ++t) {
-        const int4 r = ranges[t];
-        const int nearLo = r.x / CHIMP_FUSED_TILE, nearHi = r.y / CHIMP_FUSED_TILE;
-        int4 d = make_int4(nearLo >> CHIMP_FUSED_CHUNK_SHIFT, nearHi >> CHIMP_FUSED_CHUNK_SHIFT, 1, 0);
-        if (r.z <= r.w) {
-            d.z = (r.z / CHIMP_FUSED_TILE) >> CHIMP_FUSED_CHUNK_SHIFT;
-            d.w = (r.w / CHIMP_FUSED_TILE) >> CHIMP_FUSED_CHUNK_SHIFT;
-        }
-        // whole chunks are waited for: every tile of the last needed chunk must be ahead of this D item
-        const int needHi = std::min(nTiles - 1, (((nearHi >> CHIMP_FUSED_CHUNK_SHIFT) + 1) << CHIMP_FUSED_CHUNK_SHIFT) - 1);
-        if (r.z <= r.w) emitA(d.z << CHIMP_FUSED_CHUNK_SHIFT, std::min(nTiles - 1, ((d.w + 1) << CHIMP_FUSED_CHUNK_SHIFT) - 1));
-        emitA(d.x << CHIMP_FUSED_CHUNK_SHIFT, needHi);
-        const int target = std::min(nTiles - 1, needHi + lead);
-        while (aNext <= target) { emitA(aNext, aNext); ++aNext; }
-        deps[t] = d;
-        seq.push_back((int32_t)(0x80000000u | (unsigned)t));
-    }
-    if ((int)seq.size() != 2 * nTiles) return fail("internal error: fused sequence has %zu items for %d tiles", seq.size(), nTiles);
-    freeDev(c->d_tpSeq); freeDev(c->d_tpDeps); freeDev(c->d_tpDone); freeDev(c->d_tpTicket); freeDev(c->d_tpMom);
-    CUDA_OK(cudaMalloc(&c->d_tpSeq, seq.size() * sizeof(int32_t)));
-    CUDA_OK(cudaMalloc(&c->d_tpDeps, (size_t)nTiles * sizeof(int4)));
-    CUDA_OK(cudaMalloc(&c->d_tpDone, (size_t)nChunks * sizeof(unsigned)));
-    CUDA_OK(cudaMalloc(&c->d_tpTicket, sizeof(unsigned)));
-    CUDA_OK(cudaMalloc(&c->d_tpMom, (size_t)nTiles * sizeof(double)));
-    CUDA_OK(cudaMemcpy(c->d_tpSeq, seq.data(), seq.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(c->d_tpDeps, deps.data(), (size_t)nTiles * sizeof(int4), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemset(c->d_tpDone, 0, (size_t)nChunks * sizeof(unsigned)));
-    c->tpTiles = nTiles;
-    c->tpLaunchNo = 0;
-    c->tpReady = true;
-    c->tpMomValid = false;
-    return 0;
-}
-
-template <class L>
-void launchFused(chimp_lattice *c, const FusedArgs &fa, bool mom)
-{
-    const unsigned grid = 2u * (unsigned)fa.nTiles;
-    if (c->indexForm == CHIMP_INDEX_COMPACT) {
-        if (mom) twoPhaseFusedKernel<L, true, IDX_COMPACT><<<grid, CHIMP_FUSED_TILE, 0, c->stream>>>(fa);
-        else twoPhaseFusedKernel<L, false, IDX_COMPACT><<<grid, CHIMP_FUSED_TILE, 0, c->stream>>>(fa);
-    } else {
-        if (mom) twoPhaseFusedKernel<L, true, IDX_TABLE><<<grid, CHIMP_FUSED_TILE, 0, c->stream>>>(fa);
-        else twoPhaseFusedKernel<L, false, IDX_TABLE><<<grid, CHIMP_FUSED_TILE, 0, c->stream>>>(fa);
-    }
-    ++g_launches;
-}
-template <class L>
-void launchOutputMomentum(chimp_lattice *c, const TwoPhaseArgs &a)
-{
-    if (c->indexForm == CHIMP_INDEX_COMPACT) outputMomentumKernel<L, IDX_COMPACT><<<c->tpTiles, CHIMP_FUSED_TILE, 0, c->stream>>>(a, c->d_tpMom);
-    else outputMomentumKernel<L, IDX_TABLE><<<c->tpTiles, CHIMP_FUSED_TILE, 0, c->stream>>>(a, c->d_tpMom);
-    ++g_launches;
-}
-
-// single-rank two-phase stepping: one fused launch + the fold of the momentum partials per step
-int stepTwoPhaseFused(chimp_lattice *c, const chimp_twophase_params *p, TwoPhaseArgs &a, int n_steps)
-{
-    if (!c->tpReady && setupFused(c)) return 1;
-    FusedArgs fa{};
-    fa.seq = c->d_tpSeq;
-    fa.deps = c->d_tpDeps;
-    fa.done = c->d_tpDone;
-    fa.ticket = c->d_tpTicket;
-    fa.nTiles = c->tpTiles;
-    fa.momPartial = c->d_tpMom;
-    const double nGlobal = (double)p->n_fluid_global;
-    for (int s = 0; s < n_steps; ++s) {
-        fillPlanes(c, a.pl);
-        if (!c->tpMomValid) {
-            // the state did not come out of a collide pass (upload, initialisation): x-momentum of what it holds
-            if (c->lattice == CHIMP_D2Q9) launchOutputMomentum<D2Q9>(c, a);
-            else launchOutputMomentum<D3Q19>(c, a);
-            fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_tpMom, c->tpTiles, p->momx, nGlobal, c->d_fluxSum, c->d_forceX + c->forceNext, 1);
-            ++g_launches;
-            c->tpMomValid = true;
-        }
-        CUDA_OK(cudaMemsetAsync(c->d_tpTicket, 0, sizeof(unsigned), c->stream));
-        fa.tp = a;
-        fa.launchNo = ++c->tpLaunchNo;
-        fa.force = c->d_forceX + c->forceNext;
-        if (c->lattice == CHIMP_D2Q9) launchFused<D2Q9>(c, fa, s == n_steps - 1);
-        else launchFused<D3Q19>(c, fa, s == n_steps - 1);
-        c->forceLast = c->forceNext;
-        c->forceNext ^= 1;
-        // F_x of the next step from the populations just written (main_TWOPHASE.cpp:292-308)
-        fluxForceKernel<<<1, 256, 0, c->stream>>>(c->d_tpMom, c->tpTiles, p->momx, nGlobal, c->d_fluxSum, c->d_forceX + c->forceNext, 1);
-        ++g_launches;
-        c->cur ^= 1;
-        ++c->steps;
-    }
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-} // namespace
-} // extern "C++"
-
 int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_steps)
 {
     if (check(c, true)) return 1;
@@ -1653,12 +1509,6 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     a.beta = p->beta;
     for (int d = 0; d < 3; ++d) a.F[d] = d < c->li.nD ? p->force[d] : 0.0;
     a.forceX = c->d_forceX;
-    // opt-in (CHIMP_TP_FUSED=1): the fused launch moves 15 % fewer DRAM bytes but is latency-bound at 4 blocks/SM and
-    // measured slower than the two kernels below on B200 (profiles/r01_twophase_fused_experiment.txt)
-    const bool fused = !multi && c->lattice != CHIMP_D3Q27 && c->tpFusedEnv;
-    if (fused) return stepTwoPhaseFused(c, p, a, n_steps);
-    c->forceLast = 0;
-    c->tpMomValid = false;
     a.partial = c->d_fluxPartial;
     const unsigned gridAll = (unsigned)((c->n + 255) / 256);
     // CHIMP_TRACE=1: phase durations on the main stream (moment pass / exchange + global sum / boundary collide /
@@ -1839,7 +1689,7 @@ double chimp_last_flux_force(chimp_lattice *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     double v = 0.0;
-    cudaMemcpy(&v, c->d_forceX + c->forceLast, sizeof(double), cudaMemcpyDeviceToHost);
+    cudaMemcpy(&v, c->d_forceX, sizeof(double), cudaMemcpyDeviceToHost);
     return v;
 }
 

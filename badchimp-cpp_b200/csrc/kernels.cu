@@ -1,6 +1,5 @@
 // Non-templated helper kernels (layout conversion, halo pack/unpack, index compression).
 #include "kernels.cuh"
-#include "twophase_fused.cuh"
 
 namespace chimp {
 
@@ -134,30 +133,6 @@ __global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsig
         mean /= nGlobal;
         *forceX = 2 * (momx - mean);
     }
-}
-
-__global__ void tilePhiRangesKernel(const int32_t *__restrict__ ptable, int n, int nPad, int nQ, int window, int4 *out)
-{
-    __shared__ int r[4];
-    if (threadIdx.x == 0) { r[0] = 0x7fffffff; r[1] = -1; r[2] = 0x7fffffff; r[3] = -1; }
-    __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        int nlo = i, nhi = i, flo = 0x7fffffff, fhi = -1;
-        for (int q = 0; q < nQ; ++q) {
-            const int s = ptable[(long long)q * nPad + i];
-            if (s < 0 || s >= n) continue; // wall / ghost / zero slots are not written by the moment pass
-            const int d = s > i ? s - i : i - s;
-            if (d <= window) { nlo = min(nlo, s); nhi = max(nhi, s); }
-            else { flo = min(flo, s); fhi = max(fhi, s); }
-        }
-        atomicMin(&r[0], nlo);
-        atomicMax(&r[1], nhi);
-        atomicMin(&r[2], flo);
-        atomicMax(&r[3], fhi);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) out[blockIdx.x] = make_int4(r[0], r[1], r[2], r[3]);
 }
 
 // waits until every arrival counter selected by `mask` (bit k -> flags[k]) has reached `expect`
