@@ -38,6 +38,9 @@ void record(std::ofstream &ofs, const std::string &name, const double *p, std::u
 int main(int argc, char **argv)
 {
     if (argc < 9) { std::cerr << "usage: " << argv[0] << " mpiDir outputDir nIterations nItrWrite tau Fx Fy Fz" << std::endl; return 2; }
+#ifdef CHIMP_MPI_SHIM
+    mpishim::init(1); // oracle/mpi_shim: one in-process rank (with a real MPI this line does not exist)
+#endif
     MPI_Init(NULL, NULL);
     int nProcs;
     MPI_Comm_size(MPI_COMM_WORLD, &nProcs);
