@@ -52,7 +52,8 @@ SYMBOLS = [
     "chimp_set_exchange_callback", "chimp_set_stream", "chimp_synchronize", "chimp_num_own_nodes",
     "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_irregular_fraction",
     "chimp_index_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_step_twophase_timed", "chimp_peer_mode", "chimp_voxel_table_host", "chimp_create_from_voxels",
-    "chimp_voxel_phi_table_host", "chimp_set_phi_table_from_voxels", "chimp_init_uniform",
+    "chimp_voxel_phi_table_host", "chimp_set_phi_table_from_voxels", "chimp_slab_tables_host", "chimp_create_slab_from_voxels",
+    "chimp_halo_face_recv_count", "chimp_halo_face_recv_list", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
     "chimp_set_halo_buffers", "chimp_halo_stream", "chimp_add_halo_face", "chimp_set_boundary_count", "chimp_set_scalar_exchange_callback",
     "chimp_set_allreduce_callback", "chimp_scalar_neighbor_info", "chimp_init_equilibrium_dev", "chimp_set_phi_table_dev", "chimp_flux_force", "chimp_capillary_force", "chimp_node_list_flux", "chimp_add_scalar_halo_face", "chimp_ipc_handles_twophase", "chimp_local_pointers_twophase", "chimp_connect_peer_scalar", "chimp_connect_world", "chimp_host_scalar_halo_lists", "chimp_ipc_handles", "chimp_local_pointers", "chimp_connect_peer", "chimp_scalar_send_buffer_dev", "chimp_scalar_recv_buffer_dev",
@@ -349,7 +350,15 @@ class Lattice:
     def recv_dst(self, k):
         """slot offsets (q*plane_stride + slot) of my receive list for neighbour / face k"""
         faces = getattr(self, "_faces", None)
-        return faces[k][1] if faces else self.host_halo_lists(k)[2]
+        if faces:
+            return faces[k][1]
+        lib().chimp_halo_face_recv_count.restype = C.c_longlong
+        cnt = int(lib().chimp_halo_face_recv_count(self.h, C.c_int(k)))
+        if cnt > 0:      # structured-ingest face registered by the library itself (chimp_create_slab_from_voxels)
+            dst = np.zeros(cnt, dtype=np.int64)
+            _check(lib().chimp_halo_face_recv_list(self.h, C.c_int(k), _p(dst)))
+            return dst
+        return self.host_halo_lists(k)[2]
 
     def connect_peer(self, k, peer_field_stride, peer_face, peer_dst, handles=None, pointers=None):
         peer_dst = np.ascontiguousarray(peer_dst, dtype=np.int64)
@@ -538,6 +547,41 @@ def voxel_phi_table_host(lattice: str, voxels, wall_phi, periodic="xyz"):
     extra = np.zeros(max(n_extra.value, 1))
     _check(lib().chimp_voxel_phi_table_host(*args, _p(w), C.byref(n_extra), _p(ptable), _p(extra)))
     return ptable, n_extra.value, extra[: n_extra.value]
+
+
+def slab_tables_host(lattice: str, voxels_ext):
+    """host half of the z-slab voxel ingest (no CUDA): dict like ingest.build_slab_tables returns (numpy arrays)"""
+    v = np.ascontiguousarray(voxels_ext, dtype=np.uint8)
+    nx, ny, nze = v.shape
+    info = (C.c_longlong * 8)()
+    args = (C.c_int(G.LATTICE_ID[lattice]), C.c_int(nx), C.c_int(ny), C.c_int(nze - 2), _p(v))
+    _check(lib().chimp_slab_tables_host(*args, info, None, None, None, None, None, None))
+    n, n_pad, n_halo, n_boundary, sd, rd, su, ru = [int(x) for x in info]
+    nq = len(G.BASIS[lattice])
+    table = np.zeros((nq, n_pad), dtype=np.int32)
+    labels = np.zeros(n_pad, dtype=np.int32)
+    lists = [np.zeros(k, dtype=np.int64) for k in (sd, rd, su, ru)]
+    _check(lib().chimp_slab_tables_host(*args, info, _p(table), _p(labels), *[_p(a) for a in lists]))
+    return dict(table=table, labels=labels, n=n, n_pad=n_pad, n_halo=n_halo, n_boundary=n_boundary, stride=n_pad + n_halo,
+                faces={"down": (lists[0], lists[1]), "up": (lists[2], lists[3])})
+
+
+def slab_lattice_from_voxels(lattice: str, voxels_ext, rank_down, rank_up, index_form=INDEX_COMPACT, device=-1):
+    """chimp_create_slab_from_voxels: one rank's z-slab with its two halo faces registered"""
+    v = np.ascontiguousarray(voxels_ext, dtype=np.uint8)
+    nx, ny, nze = v.shape
+    obj = Lattice.__new__(Lattice)
+    obj.lattice = lattice
+    obj.nq = len(G.BASIS[lattice])
+    obj.nd = G.BASIS[lattice].shape[1]
+    obj.n_nodes = int(np.count_nonzero(v[:, :, 1:-1])) + 1
+    obj.n_fields = 1
+    obj._cb = None
+    obj._faces = None
+    obj.h = C.c_void_p()
+    _check(lib().chimp_create_slab_from_voxels(C.byref(obj.h), G.LATTICE_ID[lattice], C.c_int(nx), C.c_int(ny), C.c_int(nze - 2), _p(v),
+                                               C.c_int(1), C.c_int(index_form), C.c_int(device), C.c_int(rank_down), C.c_int(rank_up)))
+    return obj
 
 
 def lattice_from_voxels(lattice: str, voxels, periodic="xyz", n_fields=1, index_form=INDEX_COMPACT, device=-1, wall_phi=None):

@@ -87,6 +87,7 @@ struct Neighbor {
     long long sendCount = 0, recvCount = 0; // per field
     long long *d_sendSrc = nullptr, *d_recvDst = nullptr;
     std::vector<long long> hSrc, hPeerDst; // host copies: send list and the peer slots it lands in (fused peer tables)
+    std::vector<long long> hRecv;          // host copy of the receive list of a structured-ingest face (handed to the peer)
     long long *d_phiSendSrc = nullptr, *d_phiRecvDst = nullptr; // scalar (phi) halo: slots of the phi array
     double *d_phiSendBuf = nullptr, *d_phiRecvBuf = nullptr;
     long long phiSendCount = 0, phiRecvCount = 0;
@@ -1877,6 +1878,7 @@ int chimp_add_halo_face(chimp_lattice *c, int neig_rank, long long n_send, const
     nb.sendCount = n_send;
     nb.recvCount = n_recv;
     nb.hSrc.assign(send_src, send_src + n_send);
+    nb.hRecv.assign(recv_dst, recv_dst + n_recv);
     if (n_send) {
         CUDA_OK(cudaMalloc(&nb.d_sendSrc, (size_t)n_send * sizeof(long long)));
         CUDA_OK(cudaMemcpy(nb.d_sendSrc, send_src, (size_t)n_send * sizeof(long long), cudaMemcpyHostToDevice));
@@ -2530,6 +2532,185 @@ int chimp_set_phi_table_from_voxels(chimp_lattice *c, int nx, int ny, int nz, co
     cudaFree(d_pt);
     cudaFree(d_ex);
     return rc;
+}
+
+// ---- z-slab of a decomposition from a voxel array (host code on N GPUs) --------------------------------------
+// voxels_ext is the rank's own slab plus one layer of the neighbour below (z index 0) and above (z index nz + 1);
+// x and y are periodic, the z neighbours are other ranks (a ring; with one rank they are the slab itself).  Same
+// tables as the torch ingest (ingest.build_slab_tables, checked cell by cell in tests/test_voxel_ingest.py): own fluid
+// cells carry the reference's per-rank labels 1..N (C-order of the own slab, vtklb.py:92-94); device slots put the
+// two halo-coupled layers first and then go layer by layer; a population entering from a neighbour rank is pulled
+// from a halo-in slot numbered per direction in C-order of the receiving cells.
+extern "C++" {
+namespace {
+struct SlabTables {
+    int n = 0, nPad = 0, nHalo = 0, nBoundary = 0;
+    long long stride = 0;
+    std::vector<int32_t> table, labels, slotOfCell; // slotOfCell: [nx*ny*nz] slot of an own cell, -1 solid
+    std::vector<long long> send[2], recv[2];        // face 0 = down (towards z - 1), 1 = up
+};
+
+int buildSlabTables(int lattice, int nx, int ny, int nz, const uint8_t *ext, SlabTables &t)
+{
+    const LatInfo li = latInfo(lattice);
+    if (li.nQ == 0) return fail("unknown lattice id %d", lattice);
+    if (li.nD != 3) return fail("z-slabs need a 3-D lattice");
+    if (!ext || nx < 1 || ny < 1 || nz < 2) return fail("bad slab voxel array (at least two own layers)");
+    if ((long long)nx * ny * (nz + 2) >= (1ll << 31)) return fail("slab voxel array too large for 32-bit cell indices");
+    const int nzE = nz + 2, nQ = li.nQ;
+    auto E = [&](int x, int y, int ze) -> uint8_t { return ext[((size_t)x * ny + y) * nzE + ze]; }; // ze in [0, nz + 2)
+    auto wrapX = [&](int x) { return (x % nx + nx) % nx; };
+    auto wrapY = [&](int y) { return (y % ny + ny) % ny; };
+    // labels in C-order of the own slab
+    std::vector<int32_t> label((size_t)nx * ny * nz, 0);
+    int n = 0;
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y)
+            for (int z = 0; z < nz; ++z)
+                if (E(x, y, z + 1)) label[((size_t)x * ny + y) * nz + z] = ++n;
+    if (n == 0) return fail("the slab has no fluid cell");
+    t.n = n;
+    t.nPad = ((n + 31) / 32) * 32;
+    // slot order: layer 0, layer nz - 1, layers 1 .. nz - 2; inside a layer the C-order of (x, y)
+    t.slotOfCell.assign((size_t)nx * ny * nz, -1);
+    t.labels.assign((size_t)t.nPad, 0);
+    int slot = 0;
+    auto placeLayer = [&](int z) {
+        for (int x = 0; x < nx; ++x)
+            for (int y = 0; y < ny; ++y) {
+                const size_t cell = ((size_t)x * ny + y) * nz + z;
+                if (label[cell]) { t.slotOfCell[cell] = slot; t.labels[(size_t)slot] = label[cell]; ++slot; }
+            }
+    };
+    placeLayer(0);
+    placeLayer(nz - 1);
+    t.nBoundary = slot;
+    for (int z = 1; z < nz - 1; ++z) placeLayer(z);
+    // halo elements per direction: receiving cells of my bottom layer (c_z = +1) / top layer (c_z = -1)
+    std::vector<int> counts(nQ, 0);
+    std::vector<std::vector<int32_t>> haloNo(nQ); // [q][x*ny + y] -> k or -1
+    for (int q = 0; q < nQ; ++q) {
+        int c[3];
+        lookupC(lattice, q, c);
+        if (c[2] == 0) continue;
+        haloNo[q].assign((size_t)nx * ny, -1);
+        const int zOwn = c[2] == 1 ? 0 : nz - 1, zHalo = c[2] == 1 ? 0 : nz + 1;
+        for (int x = 0; x < nx; ++x)
+            for (int y = 0; y < ny; ++y)
+                if (E(x, y, zOwn + 1) && E(wrapX(x - c[0]), wrapY(y - c[1]), zHalo)) haloNo[q][(size_t)x * ny + y] = counts[q]++;
+    }
+    int maxCount = 0;
+    for (int q = 0; q < nQ; ++q) maxCount = std::max(maxCount, counts[q]);
+    t.nHalo = ((maxCount + 15) / 16) * 16;
+    t.stride = (long long)t.nPad + t.nHalo;
+    // pull table
+    t.table.assign((size_t)nQ * t.nPad, -1);
+    for (int q = 0; q < nQ; ++q) {
+        int c[3];
+        lookupC(lattice, q, c);
+        int32_t *row = t.table.data() + (size_t)q * t.nPad;
+        parallelOverX(nx, [&](int x0, int x1) {
+            for (int x = x0; x < x1; ++x)
+                for (int y = 0; y < ny; ++y)
+                    for (int z = 0; z < nz; ++z) {
+                        const int s = t.slotOfCell[((size_t)x * ny + y) * nz + z];
+                        if (s < 0) continue;
+                        const int zs = z - c[2];
+                        if (zs < 0 || zs >= nz) { // from the neighbour rank: halo-in slot, or a wall there
+                            const int k = haloNo[q][(size_t)x * ny + y];
+                            row[s] = k >= 0 ? t.nPad + k : -1;
+                        } else {
+                            row[s] = t.slotOfCell[((size_t)wrapX(x - c[0]) * ny + wrapY(y - c[1])) * nz + zs];
+                        }
+                    }
+        });
+    }
+    // faces: directions ascending, receiving cells in C-order of (x, y)
+    for (int q = 0; q < nQ; ++q) {
+        int c[3];
+        lookupC(lattice, q, c);
+        if (c[2] == 0) continue;
+        const int recvFace = c[2] == 1 ? 0 : 1, sendFace = 1 - recvFace;
+        for (int k = 0; k < counts[q]; ++k) t.recv[recvFace].push_back((long long)q * t.stride + t.nPad + k);
+        // what the neighbour on the other side receives from me: its cell (x, y) of the adjacent layer is fluid and
+        // my cell (x - cx, y - cy) of the layer facing it is fluid
+        const int zMine = c[2] == 1 ? nz - 1 : 0, zTheirs = c[2] == 1 ? nz + 1 : 0;
+        for (int x = 0; x < nx; ++x)
+            for (int y = 0; y < ny; ++y) {
+                if (!E(x, y, zTheirs)) continue;
+                const int xs = wrapX(x - c[0]), ys = wrapY(y - c[1]);
+                const int s = t.slotOfCell[((size_t)xs * ny + ys) * nz + zMine];
+                if (s >= 0) t.send[sendFace].push_back((long long)q * t.stride + s);
+            }
+    }
+    return 0;
+}
+} // namespace
+} // extern "C++"
+
+int chimp_slab_tables_host(int lattice, int nx, int ny, int nz_own, const uint8_t *voxels_ext, long long *info8, int32_t *table,
+                           int32_t *labels, long long *send_down, long long *recv_down, long long *send_up, long long *recv_up)
+{
+    SlabTables t;
+    if (buildSlabTables(lattice, nx, ny, nz_own, voxels_ext, t)) return 1;
+    if (info8) {
+        info8[0] = t.n; info8[1] = t.nPad; info8[2] = t.nHalo; info8[3] = t.nBoundary;
+        info8[4] = (long long)t.send[0].size(); info8[5] = (long long)t.recv[0].size();
+        info8[6] = (long long)t.send[1].size(); info8[7] = (long long)t.recv[1].size();
+    }
+    if (table) memcpy(table, t.table.data(), t.table.size() * sizeof(int32_t));
+    if (labels) memcpy(labels, t.labels.data(), t.labels.size() * sizeof(int32_t));
+    long long *dst[4] = {send_down, recv_down, send_up, recv_up};
+    const std::vector<long long> *src[4] = {&t.send[0], &t.recv[0], &t.send[1], &t.recv[1]};
+    for (int k = 0; k < 4; ++k)
+        if (dst[k] && !src[k]->empty()) memcpy(dst[k], src[k]->data(), src[k]->size() * sizeof(long long));
+    return 0;
+}
+
+int chimp_create_slab_from_voxels(chimp_lattice **out, int lattice, int nx, int ny, int nz_own, const uint8_t *voxels_ext, int n_fields,
+                                  int index_form, int device, int rank_down, int rank_up)
+{
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    if (n_fields != 1) return fail("z-slabs from voxels are offered for one-field lattices (two-field slabs: the device-table route)");
+    SlabTables t;
+    if (buildSlabTables(lattice, nx, ny, nz_own, voxels_ext, t)) return 1;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return fail("no CUDA device available: this engine has no CPU fallback");
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    CUDA_OK(cudaSetDevice(device));
+    int32_t *d_table = nullptr, *d_label = nullptr;
+    int rc = 0;
+    if (cudaMalloc(&d_table, t.table.size() * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&d_label, t.labels.size() * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemcpy(d_table, t.table.data(), t.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_label, t.labels.data(), t.labels.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail("copy of the slab tables to the device failed");
+    if (!rc) rc = chimp_create_from_device_table(out, lattice, t.n, t.nPad, t.nHalo, d_table, d_label, n_fields, index_form, device);
+    cudaFree(d_table);
+    cudaFree(d_label);
+    if (rc) return rc;
+    chimp_lattice *c = *out;
+    if (chimp_add_halo_face(c, rank_down, (long long)t.send[0].size(), t.send[0].data(), (long long)t.recv[0].size(), t.recv[0].data()) ||
+        chimp_add_halo_face(c, rank_up, (long long)t.send[1].size(), t.send[1].data(), (long long)t.recv[1].size(), t.recv[1].data()) ||
+        chimp_set_boundary_count(c, t.nBoundary)) {
+        chimp_destroy(c);
+        *out = nullptr;
+        return 1;
+    }
+    return 0;
+}
+
+long long chimp_halo_face_recv_count(chimp_lattice *c, int k)
+{
+    if (!c || k < 0 || k >= (int)c->nbrs.size()) return -1;
+    return (long long)c->nbrs[k].hRecv.size();
+}
+int chimp_halo_face_recv_list(chimp_lattice *c, int k, long long *recv_dst)
+{
+    if (!c || k < 0 || k >= (int)c->nbrs.size() || !recv_dst) return fail("bad halo face index");
+    const auto &v = c->nbrs[k].hRecv;
+    if (!v.empty()) memcpy(recv_dst, v.data(), v.size() * sizeof(long long));
+    return 0;
 }
 
 int chimp_num_own_nodes(chimp_lattice *c) { return c ? c->n : 0; }

@@ -108,6 +108,22 @@ int chimp_voxel_phi_table_host(int lattice, int nx, int ny, int nz, const uint8_
                                int *n_extra, int32_t *ptable, double *phi_extra);
 int chimp_set_phi_table_from_voxels(chimp_lattice *, int nx, int ny, int nz, const uint8_t *voxels, int periodic_mask, const double *wall_phi);
 
+/* One z-slab of an N-rank decomposition for host code: voxels_ext is uint8 [nx][ny][nz_own + 2] -- the rank's own
+ * layers plus one layer of the rank below (z index 0) and above (z index nz_own + 1); x and y are periodic, the ranks
+ * form a ring in z (rank map of relperm_input.py:16-35 with nproc = [1, 1, N]).  Own fluid cells get the reference's
+ * per-rank labels 1..N; the two halo-coupled layers occupy the leading device slots, the others follow layer by layer.
+ * The lattice comes with its two halo faces registered (face 0 towards rank_down, face 1 towards rank_up) and the
+ * boundary count set; what remains is the transport: chimp_connect_peer per face with the neighbour's handles /
+ * pointers and ITS receive list (chimp_halo_face_recv_list of the face that looks at me), or the exchange callback.
+ * chimp_slab_tables_host is the host half alone (no CUDA call): info8 = {n_own, n_pad, n_halo, n_boundary, n_send_down,
+ * n_recv_down, n_send_up, n_recv_up}; the other pointers may be NULL. */
+int chimp_slab_tables_host(int lattice, int nx, int ny, int nz_own, const uint8_t *voxels_ext, long long *info8, int32_t *table,
+                           int32_t *labels, long long *send_down, long long *recv_down, long long *send_up, long long *recv_up);
+int chimp_create_slab_from_voxels(chimp_lattice **out, int lattice, int nx, int ny, int nz_own, const uint8_t *voxels_ext, int n_fields,
+                                  int index_form, int device, int rank_down, int rank_up);
+long long chimp_halo_face_recv_count(chimp_lattice *, int k);
+int chimp_halo_face_recv_list(chimp_lattice *, int k, long long *recv_dst);
+
 void chimp_destroy(chimp_lattice *);
 
 /* ---- state transfer in reference layout and labels.

@@ -168,3 +168,71 @@ def test_cpp_voxel_case_app_reproduces_oracle_port(lattice, shape, periodic, tmp
     vel = np.frombuffer(data, dtype="<f8", count=(n + 1) * lg.nd, offset=4 + 8 * (n + 1)).reshape(n + 1, lg.nd)
     assert np.array_equal(rho[1:], pr.rho[bulk, 0])
     assert np.array_equal(vel[1:], pr.vel[bulk])
+
+
+@pytest.mark.parametrize("lattice,shape,seed", [("D3Q19", (9, 8, 5), 1), ("D3Q27", (7, 6, 4), 2), ("D3Q19", (12, 10, 2), 3), ("D3Q19", (6, 7, 9), 4)])
+def test_host_slab_tables_equal_torch_ingest(lattice, shape, seed):
+    """chimp_slab_tables_host (the host half of chimp_create_slab_from_voxels) against ingest.build_slab_tables: pull table,
+    labels, slot order (halo-coupled layers first, then layer by layer), halo sizes and the four face lists"""
+    import torch
+    pkg = helpers.load_package()
+    ingest = importlib.import_module("badchimp_cpp_b200.ingest")
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = shape
+    ext = (rng.random((nx, ny, nz + 2)) < 0.7).astype(np.uint8)
+    mine = pkg.capi.slab_tables_host(lattice, ext)
+    ref = ingest.build_slab_tables(torch.from_numpy(ext).bool(), lattice, True)
+    for key in ("n", "n_pad", "n_halo", "n_boundary", "stride"):
+        assert mine[key] == ref[key], key
+    n = mine["n"]
+    assert np.array_equal(mine["labels"], ref["labels"].numpy())
+    assert np.array_equal(mine["table"][:, :n], ref["table"].numpy()[:, :n])
+    for face in ("down", "up"):
+        for k in (0, 1):
+            assert np.array_equal(mine["faces"][face][k], ref["faces"][face][k].numpy()), (face, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lattice,world", [("D3Q19", 2), ("D3Q19", 3), ("D3Q27", 2)])
+def test_slab_lattices_from_voxels_with_peer_halos_vs_oracle_port(lattice, world):
+    """N z-slabs created by chimp_create_slab_from_voxels in one process, connected through peer memory (fused into the
+    step kernel), against the oracle port of the undecomposed geometry: bit for bit"""
+    from test_gpu_parity import _connect_in_process
+    pkg = helpers.load_package()
+    port = helpers.oracle_port()
+    nzr = 6
+    shape = (14, 12, nzr * world)
+    geo = pkg.geometry.sphere_pack(shape, 3.5, 0.6, 12).astype(np.uint8)
+    lats = []
+    for r in range(world):
+        idx = np.arange(r * nzr - 1, (r + 1) * nzr + 1) % shape[2]
+        lat = pkg.capi.slab_lattice_from_voxels(lattice, geo[:, :, idx], (r - 1) % world, (r + 1) % world)
+        lat.init_uniform(1.0)
+        lats.append(lat)
+    # ring: face 0 of rank r looks down at rank r - 1 (whose face 1 looks up at r), face 1 looks up at rank r + 1
+    for r, lat in enumerate(lats):
+        down, up = lats[(r - 1) % world], lats[(r + 1) % world]
+        lat.connect_peer(0, down.nq * down.plane_stride(), 1, down.recv_dst(1), pointers=down.local_pointers())
+        lat.connect_peer(1, up.nq * up.plane_stride(), 0, up.recv_dst(0), pointers=up.local_pointers())
+    assert all(lat.peer_mode()[0] == 2 for lat in lats), [lat.peer_mode() for lat in lats]
+    steps, tau, F = 6, 0.8, (1e-6, 3e-7, -2e-7)
+    for _ in range(steps):
+        for lat in lats:
+            lat.step_begin(tau=tau, force=F)
+        for lat in lats:
+            lat.step_end()
+    lg = pkg.geometry.LatticeGeometry(geo.astype(int), lattice, "xyz")
+    tab = lg.all_ranks()[0]
+    bulk = tab.bulk_nodes()
+    pr = port.PortRank(pkg.geometry.LATTICE_ID[lattice], tab.neigh, bulk, 1, tab.halfway_bb(tab.fluid_bnd_nodes()))
+    pr.f[:] = pkg.cases.std_case_initial_state(tab, np.ones(geo.shape))[0]
+    pr.step_std_case(steps, tau=tau, force=F)
+    glabel = (np.cumsum(geo.reshape(-1)) * geo.reshape(-1)).reshape(shape)
+    checked = 0
+    for r, lat in enumerate(lats):
+        own = geo[:, :, r * nzr:(r + 1) * nzr].astype(bool)
+        gl = glabel[:, :, r * nzr:(r + 1) * nzr][own]          # global label of my cells in local label order
+        assert np.array_equal(lat.download()[1:], pr.f[gl]), "rank %d" % r
+        checked += len(gl)
+        lat.close()
+    assert checked == len(bulk)
