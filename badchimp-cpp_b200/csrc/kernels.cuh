@@ -106,6 +106,8 @@ __device__ __forceinline__ unsigned long long awaitCounter(const unsigned long l
 {
     const volatile unsigned long long *f = flag;
     if (*f >= expect) return 0ull;
+    // a wait of this context has already given up: the run is lost, do not spend another time-out per step
+    if (error && *(volatile unsigned *)error != 0u) return 0ull;
     const unsigned long long t0 = globalTimerNs();
     unsigned long long waited = 0ull;
     while (*f < expect) {
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
         if ((int)threadIdx.x < a.peer.nFaces) {
             const unsigned long long w = awaitCounter(a.peer.flagIn + threadIdx.x, a.peer.expect, a.peer.timeoutNs, a.peer.error, 1u);
             if (a.peer.trace && w) atomicMax(a.peer.trace + 2, w);
+            __threadfence_system(); // acquire: the neighbour's stores that preceded its counter are visible to what follows
         }
         __syncthreads();
         sendMask = live ? __ldg(a.peer.mask + i) : 0u;
