@@ -9,6 +9,12 @@
  *
  * One chimp_lattice per (rank, GPU).  Not thread-safe.  Step calls are asynchronous on the
  * context's stream; download / moment / reduction calls synchronise.
+ *
+ * Environment switches, read once when a lattice is created:
+ *   CHIMP_PEER_TIMEOUT_MS  bound of every device-side wait for a neighbour rank (default 20000); a wait that gives up
+ *                          raises an error that the next synchronising call returns
+ *   CHIMP_PEER_FUSED=0     peer halos through separate push launches instead of inside the step kernel
+ *   CHIMP_TRACE=1          per-rank phase timings of N-rank stepping on stderr
  */
 #ifndef CHIMP_B200_H
 #define CHIMP_B200_H
