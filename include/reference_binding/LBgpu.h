@@ -79,6 +79,32 @@ public:
         chimp_single_params p{CHIMP_TRT, 0, tauSym, tauAnti, {F[0], F[1], DXQY::nD == 3 ? F[2] : 0.0}};
         chimpCheck(chimp_step_single(h_, &p, nSteps));
     }
+    // std_one_phase: per-node attributes of main.cpp:279-345 (forceOn, interiorDomainsLabel, addMassSource, the global
+    // 1/count per interior domain) and the density of the pressure boundary (:593); afterwards stepBGK / stepTRT run
+    // the loop of main.cpp:513-597, mass-conservation source included
+    void setOnePhaseAttributes(ScalarField &forceOn, const std::vector<int> &interiorDomainsLabel, const std::vector<lbBase_t> &addMassSource,
+                               const std::vector<lbBase_t> &massSourceScaleFactor, lbBase_t rhoW) {
+        chimpCheck(chimp_set_one_phase_attributes(h_, &forceOn(0, 0), interiorDomainsLabel.data(), addMassSource.data(),
+                                                  int(massSourceScaleFactor.size()), massSourceScaleFactor.data(), rhoW));
+    }
+    // massFluxLocal of main.cpp:606-618 from the moments of the last iteration, summed in list order
+    std::vector<lbBase_t> massFlux(const std::vector<int> &pressureFluidNodes, const std::vector<int> &fluidPhase) {
+        std::vector<lbBase_t> q(2, 0.0);
+        chimpCheck(chimp_node_list_flux(h_, int(pressureFluidNodes.size()), pressureFluidNodes.data(), fluidPhase.data(), 2, 0,
+                                        DXQY::nD - 1, q.data()));
+        return q;
+    }
+    // twophase (main_TWOPHASE.cpp): solidBnd = findSolidBndNodes(nodes) before finalize(); rho(2, size) with the
+    // wettability densities of the solid boundary nodes (:150-181) after it; then nSteps iterations of :236-392
+    void setSolidBoundary(const std::vector<int> &solidBnd) { chimpCheck(chimp_set_solid_boundary(h_, int(solidBnd.size()), solidBnd.data())); }
+    void setTwoPhaseDensity(ScalarField &rho) { chimpCheck(chimp_set_twophase_density(h_, &rho(0, 0))); }
+    void stepTwoPhase(lbBase_t tau0, lbBase_t tau1, lbBase_t sigma, lbBase_t beta, lbBase_t momx, const std::valarray<lbBase_t> &F,
+                      int numNodesGlobal, int nSteps) {
+        chimp_twophase_params p{tau0, tau1, sigma, beta, momx, {F[0], F[1], DXQY::nD == 3 ? F[2] : 0.0}, numNodesGlobal};
+        chimpCheck(chimp_step_twophase(h_, &p, nSteps));
+    }
+    void phaseField(ScalarField &cgField) { chimpCheck(chimp_download_phase_field(h_, &cgField(0, 0))); }
+    lbBase_t lastFluxForce() { return chimp_last_flux_force(h_); }
     chimp_lattice *handle() { return h_; }
 private:
     chimp_lattice *h_ = nullptr;
