@@ -1,14 +1,20 @@
-"""N ranks, one process per GPU: z-slab decomposition with halo exchange over torch.distributed.
+"""N ranks, one process per GPU: z-slab decomposition, halo transports and their one-time set-up.
 
-Replaces MonLatMpi::communicateLbField (src/lbsolver/LBmonlatmpi.h:236-297): the engine packs
-the outgoing populations of the two z-faces on the device (haloPackKernel), this module moves
-the packed buffers with NCCL send/recv on the engine's halo stream while the interior nodes
-are still being collided, and the engine unpacks them into the halo-in slots.
+Replaces MonLatMpi::communicateLbField / communicateScalarField and the MPI_Allreduce of the flux controller
+(src/lbsolver/LBmonlatmpi.h:181-297, twophase/main_TWOPHASE.cpp:299).  Two transports:
 
-The z direction is periodic, so the ranks form a ring: face "down" talks to rank-1, face "up"
-to rank+1.  With 2 ranks both faces talk to the same peer; messages between one pair of ranks
-are matched in posting order, so sends are posted (down, up) and receives (up, down): the
-peer's "down" message is what arrives at my "up" face.
+* peer memory (default, attach_ring_peer / attach_ring_twophase_peer): the ranks exchange CUDA IPC handles and receive
+  lists once over torch.distributed; afterwards the engine stores halos straight into the neighbours' memory over NVLink
+  and synchronises through arrival counters -- for single-field lattices from inside the step kernel (one launch per
+  step) -- with no NCCL call and no host callback per step;
+* NCCL (attach_ring / attach_ring_twophase): the engine packs the outgoing populations of the two z-faces
+  (haloPackKernel), this module moves the packed buffers with send/recv on the engine's halo stream while the interior
+  nodes are still being collided, and the engine unpacks them into the halo-in slots.
+
+The z direction is periodic, so the ranks form a ring: face "down" talks to rank-1, face "up" to rank+1.  With 2 ranks
+both faces talk to the same peer; NCCL messages between one pair of ranks are matched in posting order, so sends are
+posted (down, up) and receives (up, down): the peer's "down" message is what arrives at my "up" face.
+The bench harness that uses all this is bench_impl.py / workloads.py.
 """
 from __future__ import annotations
 
