@@ -2133,7 +2133,6 @@ void preloadForPeerStepping(const chimp_lattice *c)
     case CHIMP_D3Q27: compact ? preloadStepKernels<D3Q27, IDX_COMPACT>(two) : preloadStepKernels<D3Q27, IDX_TABLE>(two); break;
     }
     preloadKernel(haloPushKernel);
-    preloadKernel(waitFlagKernel);
     preloadKernel(sumWaitFoldKernel);
     preloadKernel(foldAndPushKernel);
     preloadKernel(waitFlagsKernel);

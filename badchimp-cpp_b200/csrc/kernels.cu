@@ -50,12 +50,6 @@ __global__ void haloPushKernel(double *peerX, const double *__restrict__ X, cons
     }
 }
 
-__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect, unsigned long long timeoutNs, unsigned *error)
-{
-    awaitCounter(flag, expect, timeoutNs, error, 1u);
-    __threadfence_system();
-}
-
 __global__ void invertLabelsKernel(const int32_t *__restrict__ label, int n, int32_t *__restrict__ slotOf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -697,12 +697,11 @@ __global__ void planesToAosKernel(double *aos, const double *__restrict__ planes
 
 // Peer halos: the outgoing populations are stored straight into the neighbour GPU's halo-in slots over
 // NVLink (peerX is the peer's buffer, mapped through CUDA IPC), field by field; the last block to finish
-// publishes the step number in the peer's arrival flag.  waitFlagKernel is the consumer side.
+// publishes the step number in the peer's arrival flag.  waitFlagsKernel is the consumer side.
 __global__ void haloPushKernel(double *peerX, const double *__restrict__ X, const long long *__restrict__ src,
                                const long long *__restrict__ dst, int count, int nFields, long long fieldStride,
                                long long peerFieldStride, unsigned *blockCounter, unsigned long long *peerFlag,
                                unsigned long long value);
-__global__ void waitFlagKernel(const unsigned long long *flag, unsigned long long expect, unsigned long long timeoutNs, unsigned *error);
 // one double per rank summed over all ranks through peer memory (kernels.cu)
 __global__ void sumWaitFoldKernel(const void *mail, int world, int parity, unsigned long long seq, double momx, double nGlobal,
                                   double *sumOut, double *forceX, const unsigned long long *flags, unsigned flagMask,
