@@ -3,6 +3,7 @@ rank reaches every collective and rank 0 prints exactly one JSON line with the k
 workload (strong split + secondary weak run + e2e leg) and for the workloads with other decompositions."""
 import json
 import os
+import socket
 import subprocess
 import sys
 
@@ -11,6 +12,14 @@ import pytest
 import helpers
 
 STUB = os.path.join(helpers.ROOT, "tests", "bench_flow_stub.py")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
 
 
 def _run(world, workload, port):
@@ -30,7 +39,7 @@ def _run(world, workload, port):
 
 @pytest.mark.parametrize("world,workload", [(1, "std_case"), (2, "std_case"), (3, "std_case"), (2, "twophase"), (2, "d3q27_dense"), (2, "one_phase")])
 def test_every_rank_reaches_every_collective_and_one_line_is_printed(world, workload):
-    line = _run(world, workload, 29540 + world)
+    line = _run(world, workload, _free_port())
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "parity"):
         assert key in line, key
