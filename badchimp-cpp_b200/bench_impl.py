@@ -596,8 +596,8 @@ def run_b200(args):
         import torch.distributed as dist
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         import datetime
-        # a rank that dies must take the job down quickly, not after the default 10-minute watchdog
-        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
+        # a rank that dies must take the job down quickly, not after the default 10-minute watchdog (5 minutes leave room for a slow first import on a fresh box)
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=300))
     wl = W.WORKLOADS[args.workload]
     if wl["scaling"] == "single" and world > 1:
         raise SystemExit("workload %s is defined on one GPU" % args.workload)
