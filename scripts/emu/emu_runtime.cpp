@@ -1,10 +1,13 @@
 // DEVELOPMENT TOOL (see include/cuda_runtime.h): host-side model of the CUDA execution the engine relies on.
 //   * a block's threads are ucontext fibres on the calling OS thread, scheduled round-robin; a fibre gives up the
-//     processor only in __syncthreads, a warp exchange or __nanosleep, so kernels without those run straight through
+//     processor only in __syncthreads, a warp exchange or __nanosleep, so kernels without those run straight through.
+//     A kernel whose first block never yielded is run as plain calls from then on (fast); if it yields later after
+//     all, the model stops with a message rather than guessing.
 //   * blocks run in ascending order (the hardware's dispatch order, which the fused peer step relies on for progress)
 //   * streams and events execute at issue time; cudaMalloc is an aligned host allocation with red zones that
 //     cudaFree and the library destructor check
 #include "cuda_runtime.h"
+#include <sched.h>
 #include <ucontext.h>
 #include <cstdio>
 #include <ctime>
@@ -43,7 +46,12 @@ struct BlockState {
     std::vector<Warp> warps;
     void (*tramp)(void *) = nullptr;
     void *closure = nullptr;
+    bool yielded = false;   // some thread of the current launch used a barrier / exchange / sleep
+    bool direct = false;    // threads are plain calls: no fibre to switch away from
+    ThreadCtx directCtx;
 };
+std::mutex g_kernelMu;
+std::map<const void *, bool> g_kernelYields;
 thread_local BlockState *g_bs = nullptr;
 thread_local ThreadCtx g_hostCtx;
 
@@ -60,18 +68,32 @@ void fibreMain()
 }
 } // namespace
 
-ThreadCtx &ctx() { return g_bs && g_bs->current >= 0 ? g_bs->fibres[g_bs->current].tc : g_hostCtx; }
+ThreadCtx &ctx()
+{
+    BlockState *bs = g_bs;
+    if (!bs) return g_hostCtx;
+    if (bs->direct) return bs->directCtx;
+    return bs->current >= 0 ? bs->fibres[bs->current].tc : g_hostCtx;
+}
+
+static void noteYield(BlockState *bs)
+{
+    if (bs->direct) { fprintf(stderr, "emu: a kernel classified as barrier-free reached a barrier / exchange / sleep (block %u)\n", bs->directCtx.bid.x); abort(); }
+    bs->yielded = true;
+}
 
 void yield()
 {
     BlockState *bs = g_bs;
-    if (!bs || bs->current < 0) return;
+    // a sleeping thread waits for another stream (another OS thread here), never for a thread of its own block
+    if (!bs || bs->direct || bs->current < 0) { sched_yield(); return; }
     swapcontext(&bs->fibres[bs->current].uc, &bs->sched);
 }
 
 void syncthreads()
 {
     BlockState *bs = g_bs;
+    noteYield(bs);
     const unsigned long long gen = bs->generation;
     if (++bs->arrived >= bs->alive) { bs->arrived = 0; bs->generation++; return; }
     while (bs->generation == gen) yield();
@@ -87,6 +109,7 @@ static void warpBarrier(BlockState *bs, BlockState::Warp &w, int participants)
 void warpExchange(const void *mine, void *theirs, size_t size, unsigned srcLane, unsigned mask)
 {
     BlockState *bs = g_bs;
+    noteYield(bs);
     const unsigned t = bs->fibres[bs->current].tc.tid.x;
     BlockState::Warp &w = bs->warps[t >> 5];
     const unsigned lanesHere = std::min<unsigned>(32u, bs->nThreads - (t & ~31u));
@@ -106,7 +129,7 @@ unsigned long long nowNs()
     return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
 
-void runGrid(const Cfg &cfg, void (*tramp)(void *), void *closure)
+void runGrid(const Cfg &cfg, void (*tramp)(void *), void *closure, const void *kernelId)
 {
     if (g_bs) { fprintf(stderr, "emu: nested launch\n"); abort(); }
     const unsigned nThreads = cfg.b.x * cfg.b.y * cfg.b.z;
@@ -123,9 +146,37 @@ void runGrid(const Cfg &cfg, void (*tramp)(void *), void *closure)
     g_bs = &bs;
     bs.nThreads = nThreads;
     bs.warps.assign((nThreads + 31) / 32, BlockState::Warp());
+    bs.yielded = false;
+    bs.direct = false;
+    bool known = false, yields = true;
+    {
+        std::lock_guard<std::mutex> lock(g_kernelMu);
+        auto it = g_kernelYields.find(kernelId);
+        if (it != g_kernelYields.end()) { known = true; yields = it->second; }
+    }
+    bool firstBlock = true;
     for (unsigned bz = 0; bz < cfg.g.z; ++bz)
         for (unsigned by = 0; by < cfg.g.y; ++by)
             for (unsigned bx = 0; bx < cfg.g.x; ++bx) {
+                if (!firstBlock && !known) {
+                    std::lock_guard<std::mutex> lock(g_kernelMu);
+                    g_kernelYields[kernelId] = bs.yielded;
+                    known = true;
+                    yields = bs.yielded;
+                }
+                firstBlock = false;
+                if (known && !yields) {
+                    bs.direct = true;
+                    bs.directCtx.bid = uint3{bx, by, bz};
+                    bs.directCtx.bdim = cfg.b;
+                    bs.directCtx.gdim = cfg.g;
+                    for (unsigned t = 0; t < nThreads; ++t) {
+                        bs.directCtx.tid = uint3{t % cfg.b.x, (t / cfg.b.x) % cfg.b.y, t / (cfg.b.x * cfg.b.y)};
+                        tramp(closure);
+                    }
+                    bs.direct = false;
+                    continue;
+                }
                 bs.alive = (int)nThreads;
                 bs.arrived = 0;
                 for (auto &w : bs.warps) w.arrived = 0;
@@ -155,6 +206,10 @@ void runGrid(const Cfg &cfg, void (*tramp)(void *), void *closure)
                     (void)progressed;
                 }
             }
+    if (!known) {
+        std::lock_guard<std::mutex> lock(g_kernelMu);
+        g_kernelYields[kernelId] = bs.yielded;
+    }
     g_bs = nullptr;
 }
 } // namespace emu

@@ -57,7 +57,7 @@ struct Cfg {
     cudaStream_t stream;
     Cfg(dim3 g_, dim3 b_, size_t = 0, cudaStream_t s = nullptr) : g(g_), b(b_), stream(s) {}
 };
-void runGrid(const Cfg &cfg, void (*tramp)(void *), void *closure);
+void runGrid(const Cfg &cfg, void (*tramp)(void *), void *closure, const void *kernelId);
 // stream order: the operation runs on the stream's worker after everything enqueued before it (nullptr: at once)
 void enqueue(cudaStream_t stream, std::function<void()> op);
 template <class... P>
@@ -73,7 +73,7 @@ struct Bound {
         const Cfg c = cfg;
         enqueue(c.stream, [copy, kernel, c]() {
             auto call = [&]() { std::apply(kernel, copy); };
-            runGrid(c, [](void *f) { (*static_cast<decltype(call) *>(f))(); }, &call);
+            runGrid(c, [](void *f) { (*static_cast<decltype(call) *>(f))(); }, &call, (const void *)kernel);
         });
     }
 };
