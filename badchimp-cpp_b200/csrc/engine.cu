@@ -42,6 +42,7 @@ int openIpc(const unsigned char *handle64, void **out);
 int labelRangeOf(chimp_lattice *c);
 void preloadForPeerStepping(const chimp_lattice *c);
 int buildPeerTables(chimp_lattice *c);
+int buildPhiExceptions(chimp_lattice *c);
 int checkDeviceError(chimp_lattice *c);
 void awaitPeers(chimp_lattice *c);
 std::atomic<long long> g_launches{0};
@@ -153,6 +154,9 @@ struct chimp_lattice {
     std::vector<int32_t> hPtable;
     int nPhi = 0, nSolid = 0, nGhost = 0;
     int32_t *d_ptable = nullptr;
+    int32_t *d_excInfo = nullptr, *d_exc = nullptr; // derived form of ptable (kernels.cuh, TwoPhaseArgs)
+    long long excWords = 0;
+    bool phiDerived = false, phiDerivedEnv = true;
     double *d_phi = nullptr, *d_fluxPartial = nullptr, *d_fluxSum = nullptr, *d_forceX = nullptr;
     bool densitySet = false;
     // one-phase attributes
@@ -234,6 +238,7 @@ int allocateState(chimp_lattice *c)
     };
     c->trace = envInt("CHIMP_TRACE", 0) == 1;
     c->peerFusedEnv = envInt("CHIMP_PEER_FUSED", 1) != 0;
+    c->phiDerivedEnv = envInt("CHIMP_PHI_DERIVED", 1) != 0;
     c->timeoutNs = (unsigned long long)std::max(1ll, envInt("CHIMP_PEER_TIMEOUT_MS", 20000)) * 1000000ull;
     return 0;
 }
@@ -817,6 +822,7 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
     if (allocateState(c)) return 1;
     CUDA_OK(cudaStreamSynchronize(c->stream));
     if (labelRangeOf(c)) return 1; // row range of the host arrays, so that the first transfer does not pay for it
+    if (c->d_ptable && buildPhiExceptions(c)) return 1;
     c->finalized = true;
     return 0;
 }
@@ -880,6 +886,7 @@ void chimp_destroy(chimp_lattice *c)
     freeDev(c->d_peerCounter); freeDev(c->d_trace);
     if (c->h_error) cudaFreeHost(c->h_error);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
+    freeDev(c->d_excInfo); freeDev(c->d_exc);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
     for (auto &nb : c->nbrs) {
@@ -1379,6 +1386,68 @@ int chimp_init_equilibrium_dev(chimp_lattice *c, const double *rho_dev)
     return 0;
 }
 
+extern "C++" {
+namespace {
+template <class L>
+void launchPhiExceptions(chimp_lattice *c, const TwoPhaseArgs &a, int32_t *counts, int32_t *exc)
+{
+    const unsigned grid = (unsigned)((c->n + 127) / 128);
+    if (c->indexForm == CHIMP_INDEX_COMPACT) phiExceptionKernel<L, IDX_COMPACT><<<grid, 128, 0, c->stream>>>(a, counts, exc);
+    else phiExceptionKernel<L, IDX_TABLE><<<grid, 128, 0, c->stream>>>(a, counts, exc);
+    ++g_launches;
+}
+// Derived form of the phi table (TwoPhaseArgs::excInfo / exc): wherever ptable names the slot the pull index already
+// yields -- neighbor(q, n) is an own fluid node, the pull source of direction rev(q) -- nothing is stored; the other
+// links (solid boundary nodes, ghost nodes, the zero slot) are kept per node.  Built by comparing the two on the
+// device, so whatever the caller's ptable says is what the collide pass sees; ptable itself stays for CHIMP_PHI_DERIVED=0.
+int buildPhiExceptions(chimp_lattice *c)
+{
+    freeDev(c->d_excInfo);
+    freeDev(c->d_exc);
+    c->phiDerived = false;
+    c->excWords = 0;
+    if (!c->phiDerivedEnv || !c->d_ptable || c->lattice == CHIMP_D3Q27 || c->n <= 0) return 0;
+    if (c->indexForm == CHIMP_INDEX_COMPACT ? !c->d_delta : !c->d_ktable) return 0; // index not built yet (finalize calls again)
+    TwoPhaseArgs a{};
+    a.stride = c->stride;
+    a.n = c->n;
+    a.nPad = c->nPad;
+    fillIndexView(c, a.idx);
+    a.ptable = c->d_ptable;
+    int32_t *d_counts = nullptr;
+    CUDA_OK(cudaMalloc(&d_counts, (size_t)c->nPad * sizeof(int32_t)));
+    CUDA_OK(cudaMemsetAsync(d_counts, 0, (size_t)c->nPad * sizeof(int32_t), c->stream));
+    if (c->lattice == CHIMP_D2Q9) launchPhiExceptions<D2Q9>(c, a, d_counts, nullptr);
+    else launchPhiExceptions<D3Q19>(c, a, d_counts, nullptr);
+    std::vector<int32_t> info((size_t)c->nPad, 0);
+    cudaError_t e = cudaMemcpyAsync(info.data(), d_counts, (size_t)c->nPad * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cudaFree(d_counts); return fail("phi exception count failed: %s", cudaGetErrorString(e)); }
+    long long total = 0;
+    for (int i = 0; i < c->n; ++i) {
+        const int32_t words = info[(size_t)i];
+        info[(size_t)i] = words ? (int32_t)(total + 1) : 0;
+        total += words;
+        if (total >= INT_MAX) { cudaFree(d_counts); return 0; } // offsets would not fit: keep the table form
+    }
+    // d_counts becomes excInfo
+    e = cudaMemcpyAsync(d_counts, info.data(), (size_t)c->nPad * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) { cudaFree(d_counts); return fail("phi exception offsets failed: %s", cudaGetErrorString(e)); }
+    c->d_excInfo = d_counts;
+    CUDA_OK(cudaMalloc(&c->d_exc, (size_t)std::max(total, 1ll) * sizeof(int32_t)));
+    CUDA_OK(cudaMemsetAsync(c->d_exc, 0, (size_t)std::max(total, 1ll) * sizeof(int32_t), c->stream));
+    a.excInfo = c->d_excInfo;
+    if (c->lattice == CHIMP_D2Q9) launchPhiExceptions<D2Q9>(c, a, nullptr, c->d_exc);
+    else launchPhiExceptions<D3Q19>(c, a, nullptr, c->d_exc);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(c->stream)); // info (host vector) is read by the copy above
+    c->excWords = total;
+    c->phiDerived = true;
+    return 0;
+}
+} // namespace
+} // extern "C++"
+
 int chimp_set_phi_table_dev(chimp_lattice *c, const int32_t *ptable_dev, int n_extra, const double *phi_extra_dev)
 {
     if (check(c, true)) return 1;
@@ -1401,6 +1470,7 @@ int chimp_set_phi_table_dev(chimp_lattice *c, const int32_t *ptable_dev, int n_e
     CUDA_OK(cudaMalloc(&c->d_fluxSum, sizeof(double)));
     CUDA_OK(cudaMalloc(&c->d_forceX, 4 * sizeof(double)));
     CUDA_OK(cudaMemset(c->d_forceX, 0, 4 * sizeof(double)));
+    if (buildPhiExceptions(c)) return 1;
     c->densitySet = true;
     return 0;
 }
@@ -1459,7 +1529,15 @@ void launchTwoPhaseCollide(chimp_lattice *c, const TwoPhaseArgs &a, bool mom, cu
 {
     if (a.end <= a.begin) return;
     const unsigned grid = (unsigned)((a.end - a.begin + CHIMP_TP_BLOCK - 1) / CHIMP_TP_BLOCK);
-    if (c->indexForm == CHIMP_INDEX_COMPACT) {
+    if (c->phiDerived) {
+        if (c->indexForm == CHIMP_INDEX_COMPACT) {
+            if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT, true><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
+            else twoPhaseCollideKernel<L, false, IDX_COMPACT, true><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
+        } else {
+            if (mom) twoPhaseCollideKernel<L, true, IDX_TABLE, true><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
+            else twoPhaseCollideKernel<L, false, IDX_TABLE, true><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
+        }
+    } else if (c->indexForm == CHIMP_INDEX_COMPACT) {
         if (mom) twoPhaseCollideKernel<L, true, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
         else twoPhaseCollideKernel<L, false, IDX_COMPACT><<<grid, CHIMP_TP_BLOCK, 0, st>>>(a);
     } else {
@@ -1500,6 +1578,8 @@ int chimp_step_twophase(chimp_lattice *c, const chimp_twophase_params *p, int n_
     a.nPad = c->nPad;
     fillIndexView(c, a.idx);
     a.ptable = c->d_ptable;
+    a.excInfo = c->d_excInfo;
+    a.exc = c->d_exc;
     a.phi = c->d_phi;
     a.rho = c->d_rho;
     a.vel = c->d_vel;
@@ -2120,6 +2200,8 @@ void preloadStepKernels(bool twoField)
             preloadKernel(phaseMomentsKernel<L, IDX>);
             preloadKernel(twoPhaseCollideKernel<L, false, IDX>);
             preloadKernel(twoPhaseCollideKernel<L, true, IDX>);
+            preloadKernel(twoPhaseCollideKernel<L, false, IDX, true>);
+            preloadKernel(twoPhaseCollideKernel<L, true, IDX, true>);
         }
     }
 }
@@ -2754,6 +2836,12 @@ double chimp_index_bytes_per_node(chimp_lattice *c)
     if (!c || c->n == 0) return 0.0;
     if (c->indexForm == CHIMP_INDEX_TABLE) return 4.0 * c->li.nQ;
     return (4.0 * c->nWords * c->nPad + 16.0 * c->nTiles * c->nWords + 128.0 * c->nRows) / c->n;
+}
+double chimp_phi_index_bytes_per_node(chimp_lattice *c)
+{
+    if (!c || c->n == 0 || !c->d_ptable) return 0.0;
+    if (!c->phiDerived) return 4.0 * c->li.nQ;
+    return 4.0 + 4.0 * (double)c->excWords / c->n;
 }
 long long chimp_plane_stride(chimp_lattice *c) { return c ? c->stride : 0; }
 

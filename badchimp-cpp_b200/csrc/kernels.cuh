@@ -452,6 +452,10 @@ struct TwoPhaseArgs {
     int n, nPad, begin, end;
     IndexView idx;
     const int32_t *ptable; // [nQ][nPad] phi slot of neighbor(q, n)  (LButilities.h:12-22)
+    // derived form of ptable: the phi slot of neighbor(q, n) is the pull source of direction rev(q) whenever that
+    // neighbour is an own fluid node; only the other links (solid, ghost, zero slots) are stored.
+    const int32_t *excInfo; // [nPad] 0: node has no stored link, else 1 + offset of its record in exc
+    const int32_t *exc;     // record: bit mask of the stored directions, then their phi slots in direction order
     double *phi;
     double *rho; // [2][nPad]
     double *vel; // [nD][nPad]
@@ -542,21 +546,68 @@ __global__ void invertLabelsKernel(const int32_t *__restrict__ label, int n, int
 __global__ void nodeFluxKernel(const int32_t *__restrict__ nodes, int count, const int32_t *__restrict__ slotOf, int nLabels,
                                const double *__restrict__ rho, const double *__restrict__ velComp, double *__restrict__ out);
 
-template <class L, bool MOM, int IDX>
+// Set-up of the derived phi table: compares ptable with the slot the pull index yields and records the links where
+// they differ.  counts != nullptr: counts[i] = words of node i's record (0: none); otherwise the records are written
+// at the offsets in a.excInfo.
+template <class L, int IDX>
+__global__ void __launch_bounds__(128) phiExceptionKernel(const TwoPhaseArgs a, int32_t *counts, int32_t *exc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    if ((i & ~31) >= a.n) return;
+    int s[L::nQ];
+    resolveSources<L, IDX>(a, i, live, s);
+    if (!live) return;
+    uint32_t m = 0;
+    int pt[L::nQ];
+#pragma unroll
+    for (int q = 0; q < L::nQ; ++q) {
+        pt[q] = a.ptable[(long long)q * a.nPad + i];
+        const int derived = (q == L::nQ - 1) ? i : s[reverseDir<L>(q)];
+        if ((unsigned)derived >= (unsigned)a.n || derived != pt[q]) m |= 1u << q;
+    }
+    if (counts) {
+        counts[i] = m ? 1 + __popc(m) : 0;
+    } else if (m) {
+        int32_t *rec = exc + (a.excInfo[i] - 1);
+        *rec++ = (int32_t)m;
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q)
+            if ((m >> q) & 1u) *rec++ = pt[q];
+    }
+}
+
+template <class L, bool MOM, int IDX, bool DERIVED = false>
 __global__ void __launch_bounds__(CHIMP_TP_BLOCK, CHIMP_TP_MIN_BLOCKS) twoPhaseCollideKernel(const TwoPhaseArgs a)
 {
     const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < a.end;
     if (IDX == IDX_TABLE && !live) return;
     if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return;
+    // DERIVED: the pull sources come first, the gradient's phi slots follow from them; otherwise the measured order of
+    // the table form is kept (phi slots from ptable, gradient, then the pull sources)
+    int s[L::nQ];
+    if (DERIVED) resolveSources<L, IDX>(a, i, live, s);
     // colour gradient first (LButilities.h:12-22 -> LBd3q19.h:155-163): its Q gathered scalars are reduced
     // to nD numbers before the populations occupy the registers
     double g[3] = {0.0, 0.0, 0.0};
     double CGNorm = 0.0;
     if (live) {
         double ph[L::nQ];
+        if (DERIVED) {
+            const int info = __ldg(a.excInfo + i);
+            const int32_t *rec = a.exc + (info ? info - 1 : 0);
+            const uint32_t m = info ? (uint32_t)__ldg(rec) : 0u;
 #pragma unroll
-        for (int q = 0; q < L::nQ; ++q) ph[q] = a.phi[__ldg(a.ptable + ((unsigned)q * (unsigned)a.nPad + (unsigned)i))];
+            for (int q = 0; q < L::nQ; ++q) {
+                int slot = (q == L::nQ - 1) ? i : s[reverseDir<L>(q)];
+                if ((m >> q) & 1u) slot = __ldg(rec + 1 + __popc(m & ((1u << q) - 1u)));
+                ph[q] = a.phi[slot];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < L::nQ; ++q) ph[q] = a.phi[__ldg(a.ptable + ((unsigned)q * (unsigned)a.nPad + (unsigned)i))];
+        }
         g[0] = latticeGrad<L, 0>(ph);
         g[1] = latticeGrad<L, 1>(ph);
         if (L::nD == 3) g[2] = latticeGrad<L, 2>(ph);
@@ -567,9 +618,12 @@ __global__ void __launch_bounds__(CHIMP_TP_BLOCK, CHIMP_TP_MIN_BLOCKS) twoPhaseC
     }
     double fTot[L::nQ];
     const long long field1 = (long long)L::nQ * a.stride;
-    forEachSource<L, IDX>(a, i, live, [&](int q, const double *p) {
+    if (!DERIVED) resolveSources<L, IDX>(a, i, live, s);
+#pragma unroll
+    for (int q = 0; q < L::nQ; ++q) {
+        const double *p = a.pl.in[q] + s[q];
         fTot[q] = live ? __ldg(p) + __ldg(p + field1) : 0.0;
-    });
+    }
     if (!live) return;
     const double rho0 = a.rho[i], rho1 = a.rho[(long long)a.nPad + i];
     const double rho = rho0 + rho1;

@@ -26,6 +26,7 @@ class _ToCpu(TorchFunctionMode):
         kwargs = dict(kwargs or {})
         if _is_cuda(kwargs.get("device")):
             kwargs["device"] = "cpu"
+        kwargs.pop("pin_memory", None)
         name = getattr(func, "__name__", "")
         if name == "cuda":
             return args[0]

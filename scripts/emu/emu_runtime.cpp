@@ -19,6 +19,11 @@
 #include <thread>
 #include <vector>
 
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define EMU_ASAN 1
+#endif
+
 namespace emu {
 namespace {
 constexpr size_t kStack = 256 * 1024;
@@ -46,6 +51,8 @@ struct BlockState {
     std::vector<Warp> warps;
     void (*tramp)(void *) = nullptr;
     void *closure = nullptr;
+    const void *schedStack = nullptr; // AddressSanitizer: the scheduler's stack, learned on the first switch into a fibre
+    size_t schedStackSize = 0;
     bool yielded = false;   // some thread of the current launch used a barrier / exchange / sleep
     bool direct = false;    // threads are plain calls: no fibre to switch away from
     ThreadCtx directCtx;
@@ -55,16 +62,45 @@ std::map<const void *, bool> g_kernelYields;
 thread_local BlockState *g_bs = nullptr;
 thread_local ThreadCtx g_hostCtx;
 
+// fibre -> scheduler (last == true: the fibre is finished and its stack will be reused)
+void toScheduler(BlockState *bs, Fibre &f, bool last)
+{
+#ifdef EMU_ASAN
+    void *fake = nullptr;
+    __sanitizer_start_switch_fiber(last ? nullptr : &fake, bs->schedStack, bs->schedStackSize);
+    swapcontext(&f.uc, &bs->sched);
+    __sanitizer_finish_switch_fiber(fake, &bs->schedStack, &bs->schedStackSize);
+#else
+    (void)last;
+    swapcontext(&f.uc, &bs->sched);
+#endif
+}
+// scheduler -> fibre
+void toFibre(BlockState *bs, Fibre &f)
+{
+#ifdef EMU_ASAN
+    void *fake = nullptr;
+    __sanitizer_start_switch_fiber(&fake, f.stack, kStack);
+    swapcontext(&bs->sched, &f.uc);
+    __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#else
+    swapcontext(&bs->sched, &f.uc);
+#endif
+}
+
 void fibreMain()
 {
     BlockState *bs = g_bs;
+#ifdef EMU_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, &bs->schedStack, &bs->schedStackSize);
+#endif
     Fibre &f = bs->fibres[bs->current];
     bs->tramp(bs->closure);
     f.done = true;
     bs->alive--;
     // a thread that exits no longer takes part in barriers
     if (bs->arrived > 0 && bs->arrived >= bs->alive) { bs->arrived = 0; bs->generation++; }
-    swapcontext(&f.uc, &bs->sched);
+    toScheduler(bs, f, true);
 }
 } // namespace
 
@@ -87,7 +123,7 @@ void yield()
     BlockState *bs = g_bs;
     // a sleeping thread waits for another stream (another OS thread here), never for a thread of its own block
     if (!bs || bs->direct || bs->current < 0) { sched_yield(); return; }
-    swapcontext(&bs->fibres[bs->current].uc, &bs->sched);
+    toScheduler(bs, bs->fibres[bs->current], false);
 }
 
 void syncthreads()
@@ -199,7 +235,7 @@ void runGrid(const Cfg &cfg, void (*tramp)(void *), void *closure, const void *k
                     for (unsigned t = 0; t < nThreads; ++t) {
                         if (fs[t].done) continue;
                         bs.current = (int)t;
-                        swapcontext(&bs.sched, &fs[t].uc);
+                        toFibre(&bs, fs[t]);
                         bs.current = -1;
                         if (fs[t].done) { --remaining; ++progressed; }
                     }

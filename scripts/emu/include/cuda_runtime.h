@@ -112,6 +112,7 @@ template <class T> static inline T atomicMax(T *p, T v)
     while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 using std::max;
 using std::min;
 

@@ -206,3 +206,46 @@ def test_twophase_step_does_not_depend_on_how_a_run_is_split_into_calls(lattice,
     for a, b in zip(one[:4], table[:4]):
         assert np.allclose(a, b, rtol=1e-13, atol=1e-16)
     assert abs(one[4] - table[4]) <= 1e-12 * abs(one[4])
+
+
+@pytest.mark.parametrize("lattice,shape,periodic,index_form", [("D3Q19", (36, 30, 32), "xyz", 1), ("D3Q19", (26, 30, 24), "x", 0), ("D2Q9", (200, 160), "xy", 1)])
+def test_twophase_derived_phi_index_gives_the_bits_of_the_phi_table(lattice, shape, periodic, index_form, monkeypatch):
+    """The collide pass locates phi of neighbor(q, n) (colour gradient, LButilities.h:12-22) either through the full
+    table (CHIMP_PHI_DERIVED=0, 4 nQ bytes per node) or through its derived form (default: the pull source of rev(q),
+    plus the stored links at solid / ghost / zero slots).  Both must select the same slots: every field is bit-identical
+    after 15 steps, and the derived form is the one in use and an order of magnitude smaller."""
+    pkg = helpers.load_package()
+    geo = pkg.geometry.sphere_pack(shape, 4.0, 0.5, 23).astype(int)
+    if periodic == "x":
+        geo[:, 0] = geo[:, -1] = 0
+        geo[:, :, 0] = geo[:, :, -1] = 0
+    x = np.arange(shape[0]).reshape((-1,) + (1,) * (len(shape) - 1)) * np.ones(shape)
+    rho0 = (x < shape[0] / 2).astype(float)
+    lg = pkg.geometry.LatticeGeometry(geo, lattice, periodic)
+    t = lg.all_ranks()[0]
+    setup = pkg.cases.two_phase_setup(lg, [t], rho0, 1.0 - rho0, 0.3 * (geo == 0))[0]
+    bulk = t.bulk_nodes()
+    args = (1.0, 0.8, 0.01, 1.0, 1e-5, (0, 1e-7, 0), len(bulk))
+    nq = {"D3Q19": 19, "D2Q9": 9}[lattice]
+
+    def run(derived):
+        monkeypatch.setenv("CHIMP_PHI_DERIVED", "1" if derived else "0")   # read when the lattice is created
+        lat = pkg.capi.Lattice.from_rank_tables(t, n_fields=2)
+        lat.add_halfway_bb(*t.halfway_bb(bulk))
+        lat.set_solid_boundary(setup["solid_bnd"])
+        lat.finalize(index_form)
+        lat.set_twophase_density(setup["rho"])
+        lat.upload(setup["f0"])
+        lat.step_twophase(15, *args)
+        out = (lat.download()[bulk], lat.download_rho()[bulk], lat.download_phase_field()[bulk], lat.download_vel()[bulk], lat.last_flux_force())
+        size = lat.phi_index_bytes_per_node()
+        lat.close()
+        return out, size
+
+    table, table_bytes = run(False)
+    derived, derived_bytes = run(True)
+    assert table_bytes == 4.0 * nq
+    assert 4.0 <= derived_bytes < 0.5 * table_bytes, derived_bytes
+    for a, b in zip(table[:4], derived[:4]):
+        assert np.array_equal(a, b)
+    assert table[4] == derived[4]
