@@ -520,6 +520,8 @@ def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, p
              "ms_per_step": ms / args.steps, "value": n * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS",
              "roofline": {"bytes_per_node": wl["b_alg"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
              "index_bytes_per_node": rl.lat.index_bytes_per_node(), "irregular_tile_fraction": rl.lat.irregular_fraction()}
+        if rl.lat.n_fields == 2:
+            e["phi_index_bytes_per_node"] = rl.lat.phi_index_bytes_per_node()
         if extra:
             e.update(extra)
         return e
@@ -647,6 +649,7 @@ def run_b200(args):
         except Exception as exc:  # pragma: no cover
             e2e_rho = {"value": None, "unit": "MLUPS", "error": str(exc)}
     irregular, index_bytes = rl.lat.irregular_fraction(), rl.lat.index_bytes_per_node()
+    phi_index_bytes = rl.lat.phi_index_bytes_per_node() if rl.lat.n_fields == 2 else None
     halo_bytes, halo_mode = rl.halo_bytes, rl.halo_mode
     others = None
     if world == 1 and args.workload == "std_case" and not args.size and not args.no_extra_workloads:
@@ -695,6 +698,8 @@ def run_b200(args):
                   "l2_policy": "state per GPU 2 x %.2f GB >> 126 MB L2 (inputs larger than L2)" % (n_total / world * b_alg / 2 / 1e9),
                   "irregular_tile_fraction": irregular, "index_bytes_per_node": index_bytes, "setup_seconds": setup_s,
                   "mean_rho_error": m["mass_err"]}
+        if phi_index_bytes is not None:
+            config["phi_index_bytes_per_node"] = phi_index_bytes
         if args.interior_domains:
             config["interior_domains"] = "two interior domains with mass sources: per-step mass-change sum active"
         if world > 1:
