@@ -522,6 +522,8 @@ def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, p
              "index_bytes_per_node": rl.lat.index_bytes_per_node(), "irregular_tile_fraction": rl.lat.irregular_fraction()}
         if rl.lat.n_fields == 2:
             e["phi_index_bytes_per_node"] = rl.lat.phi_index_bytes_per_node()
+        if wl["physics"] == "one_phase":
+            e["attribute_bytes_per_node"] = rl.lat.one_phase_attribute_bytes_per_node()
         if extra:
             e.update(extra)
         return e
@@ -650,6 +652,7 @@ def run_b200(args):
             e2e_rho = {"value": None, "unit": "MLUPS", "error": str(exc)}
     irregular, index_bytes = rl.lat.irregular_fraction(), rl.lat.index_bytes_per_node()
     phi_index_bytes = rl.lat.phi_index_bytes_per_node() if rl.lat.n_fields == 2 else None
+    attr_bytes = rl.lat.one_phase_attribute_bytes_per_node() if wl["physics"] == "one_phase" else None
     halo_bytes, halo_mode = rl.halo_bytes, rl.halo_mode
     others = None
     if world == 1 and args.workload == "std_case" and not args.size and not args.no_extra_workloads:
@@ -700,6 +703,8 @@ def run_b200(args):
                   "mean_rho_error": m["mass_err"]}
         if phi_index_bytes is not None:
             config["phi_index_bytes_per_node"] = phi_index_bytes
+        if attr_bytes is not None:
+            config["attribute_bytes_per_node"] = attr_bytes
         if args.interior_domains:
             config["interior_domains"] = "two interior domains with mass sources: per-step mass-change sum active"
         if world > 1:

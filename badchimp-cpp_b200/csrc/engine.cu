@@ -143,6 +143,8 @@ struct chimp_lattice {
     int labelMin = 0, labelMax = -1;
     bool labelsContiguous = false;
     uint32_t *d_delta = nullptr, *d_pmask = nullptr;
+    uint32_t *d_attr = nullptr; // one_phase attributes packed into one word per node (kernels.cuh, StepArgs::attr), if they pack
+    bool attrPackEnv = true;
     int nWords = 0;
     int32_t *d_base = nullptr, *d_rows = nullptr;
     int nTiles = 0, nRows = 0;
@@ -239,6 +241,7 @@ int allocateState(chimp_lattice *c)
     c->trace = envInt("CHIMP_TRACE", 0) == 1;
     c->peerFusedEnv = envInt("CHIMP_PEER_FUSED", 1) != 0;
     c->phiDerivedEnv = envInt("CHIMP_PHI_DERIVED", 1) != 0;
+    c->attrPackEnv = envInt("CHIMP_ATTR_PACKED", 1) != 0;
     c->timeoutNs = (unsigned long long)std::max(1ll, envInt("CHIMP_PEER_TIMEOUT_MS", 20000)) * 1000000ull;
     return 0;
 }
@@ -325,7 +328,7 @@ int setupStreams(chimp_lattice *c)
     return 0;
 }
 
-template <class L, int COLL, bool ONEPHASE, int IDX>
+template <class L, int COLL, int ONEPHASE, int IDX>
 void launchSingle(const StepArgs &a, bool mom, cudaStream_t s)
 {
     const int count = a.end - a.begin;
@@ -344,16 +347,15 @@ void launchSingle(const StepArgs &a, bool mom, cudaStream_t s)
 template <class L>
 void dispatchSingle(const chimp_lattice *c, const StepArgs &a, int coll, bool mom, cudaStream_t s)
 {
-    const bool op = c->onePhase;
+    const int op = !c->onePhase ? OP_NONE : (a.attr ? OP_PACKED : OP_ARRAYS);
     const bool rk = c->indexForm == CHIMP_INDEX_COMPACT;
 #define CH_LAUNCH(COLL, OP, IDX) launchSingle<L, COLL, OP, IDX>(a, mom, s)
-    if (coll == CHIMP_BGK) {
-        if (op) { if (rk) CH_LAUNCH(COLL_BGK, true, IDX_COMPACT); else CH_LAUNCH(COLL_BGK, true, IDX_TABLE); }
-        else    { if (rk) CH_LAUNCH(COLL_BGK, false, IDX_COMPACT); else CH_LAUNCH(COLL_BGK, false, IDX_TABLE); }
-    } else {
-        if (op) { if (rk) CH_LAUNCH(COLL_TRT, true, IDX_COMPACT); else CH_LAUNCH(COLL_TRT, true, IDX_TABLE); }
-        else    { if (rk) CH_LAUNCH(COLL_TRT, false, IDX_COMPACT); else CH_LAUNCH(COLL_TRT, false, IDX_TABLE); }
-    }
+#define CH_INDEX(COLL, OP) do { if (rk) CH_LAUNCH(COLL, OP, IDX_COMPACT); else CH_LAUNCH(COLL, OP, IDX_TABLE); } while (0)
+#define CH_ATTR(COLL) do { if (op == OP_PACKED) CH_INDEX(COLL, OP_PACKED); else if (op == OP_ARRAYS) CH_INDEX(COLL, OP_ARRAYS); else CH_INDEX(COLL, OP_NONE); } while (0)
+    if (coll == CHIMP_BGK) CH_ATTR(COLL_BGK);
+    else CH_ATTR(COLL_TRT);
+#undef CH_ATTR
+#undef CH_INDEX
 #undef CH_LAUNCH
 }
 
@@ -878,7 +880,7 @@ void chimp_destroy(chimp_lattice *c)
     if (!c) return;
     if (c->device >= 0) cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    freeDev(c->d_table); freeDev(c->d_ktable); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask);
+    freeDev(c->d_table); freeDev(c->d_ktable); freeDev(c->d_label); freeDev(c->d_delta); freeDev(c->d_pmask); freeDev(c->d_attr);
     freeDev(c->d_base); freeDev(c->d_rows); freeDev(c->d_f[0]); freeDev(c->d_f[1]);
     freeDev(c->d_rho); freeDev(c->d_vel); freeDev(c->d_flags); freeDev(c->d_slotOf);
     freeDev(c->d_mail); freeDev(c->d_peerMail);
@@ -1084,6 +1086,25 @@ int chimp_set_one_phase_attributes(chimp_lattice *c, const double *force_on, con
     c->scalePerLabel.assign(scale_per_label, scale_per_label + n_labels);
     c->rhoW = rho_w;
     c->onePhase = true;
+    // One word per node instead of four arrays (24 -> 4 bytes per node and step) when the switches are exactly 0.0 / 1.0
+    // (they are integers in the reference's input, std_one_phase/main.cpp:337-346), at most 16 labels, and the link
+    // mask fits: bit 0 forceOn, bit 1 addSource, bits 2-5 label, bits 6.. pmask (nQ - 1 <= 26 directions).
+    freeDev(c->d_attr);
+    bool packs = c->attrPackEnv && n_labels <= 16 && c->li.nQ - 1 <= 26;
+    for (int i = 0; i < c->n && packs; ++i) packs = (on[i] == 0.0 || on[i] == 1.0) && (add[i] == 0.0 || add[i] == 1.0);
+    if (packs) {
+        std::vector<uint32_t> pmask(c->nPad, 0u);
+        if (c->hasPressure && c->d_pmask) CUDA_OK(cudaMemcpy(pmask.data(), c->d_pmask, (size_t)c->nPad * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> attr(c->nPad, 0u);
+        for (int i = 0; i < c->n && packs; ++i) {
+            if (pmask[i] >> 26) packs = false; // a link bit beyond direction 25 (cannot happen: the rest direction has no link)
+            attr[i] = (on[i] == 1.0 ? 1u : 0u) | (add[i] == 1.0 ? 2u : 0u) | ((uint32_t)lab[i] << 2) | (pmask[i] << 6);
+        }
+        if (packs) {
+            CUDA_OK(cudaMalloc(&c->d_attr, attr.size() * sizeof(uint32_t)));
+            CUDA_OK(cudaMemcpy(c->d_attr, attr.data(), attr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+    }
     return 0;
 }
 
@@ -1136,6 +1157,7 @@ int fillStepArgs(chimp_lattice *c, const chimp_single_params *p, StepArgs &a)
     a.label = c->d_labelAttr;
     a.srcPerLabel = c->d_srcPerLabel;
     a.pmask = c->hasPressure ? c->d_pmask : nullptr;
+    a.attr = c->d_attr;
     a.rhoW = c->rhoW;
     a.rho = c->d_rho;
     a.vel = c->d_vel;
@@ -2173,27 +2195,26 @@ void preloadKernel(K kernel)
     cudaFuncAttributes attr;
     cudaFuncGetAttributes(&attr, kernel);
 }
+template <class L, int IDX, int OP>
+void preloadOnePhaseForms()
+{
+    preloadKernel(collideStreamKernel<L, COLL_BGK, OP, false, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_BGK, OP, true, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_TRT, OP, false, IDX>);
+    preloadKernel(collideStreamKernel<L, COLL_TRT, OP, true, IDX>);
+    if constexpr (IDX == IDX_COMPACT) {
+        preloadKernel(collideStreamKernel<L, COLL_BGK, OP, false, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_BGK, OP, true, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, OP, false, IDX_COMPACT, true>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, OP, true, IDX_COMPACT, true>);
+    }
+}
 template <class L, int IDX>
 void preloadStepKernels(bool twoField)
 {
-    preloadKernel(collideStreamKernel<L, COLL_BGK, false, false, IDX>);
-    preloadKernel(collideStreamKernel<L, COLL_BGK, false, true, IDX>);
-    preloadKernel(collideStreamKernel<L, COLL_TRT, false, false, IDX>);
-    preloadKernel(collideStreamKernel<L, COLL_TRT, false, true, IDX>);
-    preloadKernel(collideStreamKernel<L, COLL_BGK, true, false, IDX>);
-    preloadKernel(collideStreamKernel<L, COLL_BGK, true, true, IDX>);
-    preloadKernel(collideStreamKernel<L, COLL_TRT, true, false, IDX>);
-    preloadKernel(collideStreamKernel<L, COLL_TRT, true, true, IDX>);
-    if constexpr (IDX == IDX_COMPACT) {
-        preloadKernel(collideStreamKernel<L, COLL_BGK, false, false, IDX_COMPACT, true>);
-        preloadKernel(collideStreamKernel<L, COLL_BGK, false, true, IDX_COMPACT, true>);
-        preloadKernel(collideStreamKernel<L, COLL_TRT, false, false, IDX_COMPACT, true>);
-        preloadKernel(collideStreamKernel<L, COLL_TRT, false, true, IDX_COMPACT, true>);
-        preloadKernel(collideStreamKernel<L, COLL_BGK, true, false, IDX_COMPACT, true>);
-        preloadKernel(collideStreamKernel<L, COLL_BGK, true, true, IDX_COMPACT, true>);
-        preloadKernel(collideStreamKernel<L, COLL_TRT, true, false, IDX_COMPACT, true>);
-        preloadKernel(collideStreamKernel<L, COLL_TRT, true, true, IDX_COMPACT, true>);
-    }
+    preloadOnePhaseForms<L, IDX, OP_NONE>();
+    preloadOnePhaseForms<L, IDX, OP_ARRAYS>();
+    preloadOnePhaseForms<L, IDX, OP_PACKED>();
     preloadKernel(massChangeKernel<L, IDX>);
     if constexpr (L::id != D3Q27::id) {
         if (twoField) {
@@ -2836,6 +2857,11 @@ double chimp_index_bytes_per_node(chimp_lattice *c)
     if (!c || c->n == 0) return 0.0;
     if (c->indexForm == CHIMP_INDEX_TABLE) return 4.0 * c->li.nQ;
     return (4.0 * c->nWords * c->nPad + 16.0 * c->nTiles * c->nWords + 128.0 * c->nRows) / c->n;
+}
+double chimp_one_phase_attribute_bytes_per_node(chimp_lattice *c)
+{
+    if (!c || !c->onePhase) return 0.0;
+    return c->d_attr ? 4.0 : 24.0;
 }
 double chimp_phi_index_bytes_per_node(chimp_lattice *c)
 {

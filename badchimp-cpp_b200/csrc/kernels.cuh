@@ -46,6 +46,8 @@ namespace chimp {
 #endif
 
 enum { COLL_BGK = 0, COLL_TRT = 1 };
+// one_phase variant of the single-field kernel: per-node attributes from four arrays (24 B/node) or from one packed word
+enum { OP_NONE = 0, OP_ARRAYS = 1, OP_PACKED = 2 };
 enum { IDX_TABLE = 0, IDX_COMPACT = 1 };
 
 // The step kernels address one plane as  in[q] + s  with a signed 32-bit slot index s.  A bounce
@@ -138,6 +140,8 @@ struct StepArgs {
     const int32_t *label;      // [nPad] interior-domain label
     const double *srcPerLabel; // [nLabels] = 0.9*2*scale[label]*massChange[label]
     const uint32_t *pmask;     // [nPad] bit q: X[q][n] carries the anti-bounce-back value (main.cpp:155-174)
+    const uint32_t *attr;      // [nPad] ONEPHASE == OP_PACKED: the four arrays above in one word per node --
+                               //   bit 0 forceOn, bit 1 addSource (both exactly 0.0 / 1.0), bits 2-5 label, bits 6.. pmask
     double rhoW;
     // optional outputs
     double *rho; // [nPad]
@@ -231,7 +235,7 @@ struct Gather {
 // / anti-bounce-back pressure links (one_phase variant), optional moment output.
 // Reference loop bodies: std_case/main.cpp:110-135, std_one_phase/main.cpp:534-575.
 // ---------------------------------------------------------------------------------------
-template <class L, int COLL, bool ONEPHASE, bool MOM, int IDX, bool PEER = false>
+template <class L, int COLL, int ONEPHASE, bool MOM, int IDX, bool PEER = false>
 __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKernel(const StepArgs a)
 {
     const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,9 +265,20 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
     double rho = nodeRho<L>(f);
     double F[3] = {a.F[0], a.F[1], a.F[2]};
     double qSrc = 0.0;
+    uint32_t pm = 0;
     if (ONEPHASE) {
-        const double on = a.forceOn[i];
-        qSrc = a.srcPerLabel[a.label[i]] * a.addSource[i];
+        double on;
+        if (ONEPHASE == OP_PACKED) {
+            // the same products as below with the 0.0 / 1.0 factors rebuilt from their bits
+            const uint32_t w = __ldg(a.attr + i);
+            on = (w & 1u) ? 1.0 : 0.0;
+            qSrc = a.srcPerLabel[(w >> 2) & 15u] * ((w & 2u) ? 1.0 : 0.0);
+            pm = w >> 6;
+        } else {
+            on = a.forceOn[i];
+            qSrc = a.srcPerLabel[a.label[i]] * a.addSource[i];
+            if (a.pmask) pm = a.pmask[i];
+        }
         rho += 0.5 * qSrc;
 #pragma unroll
         for (int d = 0; d < L::nD; ++d) F[d] = F[d] * on;
@@ -281,8 +296,6 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
 
     const double u2 = dotD<L>(u, u);
     const double uF = dotD<L>(u, F);
-    uint32_t pm = 0;
-    if (ONEPHASE && a.pmask) pm = a.pmask[i];
 
     // Opposite directions are collided together.  With c_r = -c_q every intermediate of the
     // reversed direction is the exact IEEE negation (c.u, c.F, 3 c.u, 3 c.F, the TRT odd part) or

@@ -15,6 +15,7 @@
  *                          raises an error that the next synchronising call returns
  *   CHIMP_PEER_FUSED=0     peer halos through separate push launches instead of inside the step kernel
  *   CHIMP_TRACE=1          per-rank phase timings of N-rank stepping on stderr
+ *   CHIMP_ATTR_PACKED=0    one_phase step kernel reads its per-node attributes from four arrays instead of one packed word
  *   CHIMP_PHI_DERIVED=0    two-phase collide pass reads the full phi table (4 nQ bytes per node) instead of its derived form
  */
 #ifndef CHIMP_B200_H
@@ -290,6 +291,10 @@ int chimp_num_own_nodes(chimp_lattice *);
 double chimp_irregular_fraction(chimp_lattice *);
 /* device bytes of index data read per node per step, and of population data */
 double chimp_index_bytes_per_node(chimp_lattice *);
+/* one_phase lattices: bytes per node and step of the per-node attributes the step kernel reads (force switch, source
+ * switch, interior label, link mask): 4 when they pack into one word (switches exactly 0 / 1, at most 16 labels;
+ * CHIMP_ATTR_PACKED=0 keeps the arrays), 24 as four arrays, 0 before chimp_set_one_phase_attributes */
+double chimp_one_phase_attribute_bytes_per_node(chimp_lattice *);
 /* two-field lattices: device bytes per node per step of the index that locates phi of neighbor(q, n) for the colour
  * gradient (LButilities.h:12-22): 4 nQ for the table, 4 + 4 (stored words) / n for the derived form (the slot is
  * the pull source of rev(q) unless the link is stored; CHIMP_PHI_DERIVED=0 keeps the table); 0 without a phi table */

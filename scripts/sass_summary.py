@@ -9,8 +9,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "badchimp-cpp_b200", "libchimp_b200.so")
 KERNELS = {
-    "default single-GPU step kernel  collideStreamKernel<D3Q19, BGK, ONEPHASE=0, MOM=0, IDX_COMPACT, PEER=0>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELb0ELb0ELi1ELb0EEEvNS_8StepArgsE",
-    "N-GPU step kernel (peer exchange fused)  collideStreamKernel<D3Q19, BGK, 0, 0, IDX_COMPACT, PEER=1>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELb0ELb0ELi1ELb1EEEvNS_8StepArgsE",
+    "default single-GPU step kernel  collideStreamKernel<D3Q19, BGK, ONEPHASE=0, MOM=0, IDX_COMPACT, PEER=0>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELi0ELb0ELi1ELb0EEEvNS_8StepArgsE",
+    "N-GPU step kernel (peer exchange fused)  collideStreamKernel<D3Q19, BGK, 0, 0, IDX_COMPACT, PEER=1>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELi0ELb0ELi1ELb1EEEvNS_8StepArgsE",
 }
 HEADER = """# r02: SASS of the step kernels (cuobjdump -sass / -res-usage of badchimp-cpp_b200/libchimp_b200.so, sm_100a, nvcc 12.9,
 # -O3 -fmad=false -lineinfo; scripts/sass_summary.py).  Opcode histogram, resources, and the instructions that touch global memory.

@@ -47,6 +47,8 @@ class FakeLat:
     def download(self): return np.zeros((self.n_nodes, self.n_fields, self.nq))
     def irregular_fraction(self): return 0.01
     def index_bytes_per_node(self): return 23.5
+    def phi_index_bytes_per_node(self): return 6.0
+    def one_phase_attribute_bytes_per_node(self): return 4.0
     def peer_mode(self): return (2, "")
     def _single_params(self, *a): return capi.SingleParams()
     def close(self): pass

@@ -160,6 +160,40 @@ def test_one_phase_vs_reference(index_form):
         assert np.allclose(mass, g.rec(0, "step%d.massChange" % step), rtol=1e-9, atol=1e-16)
 
 
+@pytest.mark.parametrize("name,trt", [("onephase_d3q19_p1", False), ("onephase_d3q19_p1", True)])
+def test_one_phase_packed_attribute_word_gives_the_bits_of_the_four_arrays(name, trt, monkeypatch):
+    """The one_phase step kernel reads force switch, source switch, interior label and pressure-link mask either from
+    four arrays (24 B/node, CHIMP_ATTR_PACKED=0) or from one packed word (default when the switches are 0 / 1, as in
+    the reference's input).  Same products, same bits: populations, rho, u and the mass change agree exactly, with
+    solid / pressure / fluid-fluid links and interior-domain sources active."""
+    g = helpers.Golden(name)
+    pkg = helpers.load_package()
+    lg, tabs = helpers.build_tables(g)
+    setup = helpers.one_phase_setup(g, lg, tabs)[0]
+    bulk = tabs[0].bulk_nodes()
+
+    def run(packed):
+        monkeypatch.setenv("CHIMP_ATTR_PACKED", "1" if packed else "0")    # read when the lattice is created
+        lat = build_engine_tables(g, lg, tabs, False)[0]
+        lat.finalize(1)
+        lat.set_one_phase_attributes(setup["force_on"], setup["interior"], setup["add_source"], setup["scale"], g.args.get("rhow", 1.0))
+        lat.upload(setup["f0"])
+        kw = dict(tau=g.args["tau"], force=g.force())
+        if trt:
+            kw["trt"] = (g.args["tau"], 1.125)
+        lat.step_single(12, **kw)
+        out = (lat.download()[bulk], lat.download_rho()[bulk], lat.download_vel()[bulk], lat.download_mass_change(len(setup["scale"])))
+        size = lat.one_phase_attribute_bytes_per_node()
+        lat.close()
+        return out, size
+
+    arrays, arrays_bytes = run(False)
+    packed, packed_bytes = run(True)
+    assert (arrays_bytes, packed_bytes) == (24.0, 4.0)
+    for a, b in zip(arrays, packed):
+        assert np.array_equal(a, b)
+
+
 def test_one_phase_without_interior_domains_is_bit_exact():
     """with no interior domains the mass source vanishes and no reduction enters: bit-exact vs the oracle"""
     pkg = helpers.load_package()
