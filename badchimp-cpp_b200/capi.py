@@ -44,7 +44,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 SYMBOLS = [
     "chimp_last_error", "chimp_version", "chimp_launch_count", "chimp_lattice_nq", "chimp_lattice_nd",
     "chimp_lattice_c", "chimp_lattice_w", "chimp_lattice_reverse", "chimp_create", "chimp_add_halfway_bb",
-    "chimp_add_links", "chimp_add_neighbor", "chimp_set_solid_boundary", "chimp_build_host", "chimp_finalize",
+    "chimp_add_links", "chimp_add_constant_links", "chimp_add_neighbor", "chimp_set_solid_boundary", "chimp_build_host", "chimp_finalize",
     "chimp_create_from_device_table", "chimp_destroy", "chimp_upload_lbfield", "chimp_download_lbfield",
     "chimp_download_rho", "chimp_download_vel", "chimp_set_one_phase_attributes", "chimp_step_single",
     "chimp_set_twophase_density", "chimp_step_twophase", "chimp_download_phase_field", "chimp_last_flux_force",
@@ -155,6 +155,14 @@ class Lattice:
     def add_links(self, kind, links4):
         links4 = _i32(links4).reshape(-1, 4)
         _check(lib().chimp_add_links(self.h, C.c_int(kind), C.c_int(len(links4)), _p(links4)))
+
+    def add_constant_links(self, node_q, values):
+        """PressureBnd / InletOutlet (LBpressurebnd.h:10-88): f(q_k, node_k) = values_k after every step's boundary phase;
+        node_q is [n, 2] (destination node label, direction)"""
+        nq = np.ascontiguousarray(node_q, dtype=np.int32).reshape(-1, 2)
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+        assert len(nq) == len(v)
+        _check(lib().chimp_add_constant_links(self.h, C.c_int(len(v)), _p(nq), _p(v)))
 
     def add_neighbor(self, rank, send_nodes, send_ndir, send_dirs, recv_nodes, recv_ndir, recv_dirs):
         a = [_i32(x) for x in (send_nodes, send_ndir, send_dirs, recv_nodes, recv_ndir, recv_dirs)]

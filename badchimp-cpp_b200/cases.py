@@ -134,3 +134,57 @@ def one_phase_mass_flux(lat, setup, old=(0.0, 0.0)):
     q = 0.5 * local
     change = (q - np.asarray(old)) / (q + 1e-15)
     return local, q, change
+
+
+def _c_dot_all(lattice: str, v):
+    """cDotAll of the lattice structs (LBd2q9.h / LBd3q19.h:129-153): for every direction the signed components of v
+    added up in axis order -- the first non-zero component starts the sum, so no 0.0 enters it"""
+    basis = G.BASIS[lattice]
+    out = np.zeros(len(basis))
+    for q, c in enumerate(basis):
+        s, first = 0.0, True
+        for d, cq in enumerate(c):
+            if cq == 0:
+                continue
+            if first:
+                s, first = (v[d] if cq > 0 else -v[d]), False
+            else:
+                s = s + v[d] if cq > 0 else s - v[d]
+        out[q] = s
+    return out
+
+
+def library_bnd_links(tab: G.RankTables, bnd_nodes, kind, rho_bnd=None, rho=1.0, vel=(0.0, 0.0, 0.0), field_no=0):
+    """The stores PressureBnd<DXQY>::apply ("pressure", LBpressurebnd.h:19-41) or InletOutlet<DXQY>::apply
+    ("inletoutlet", :51-88) perform on the boundary nodes `bnd_nodes` (classed by Boundary<DXQY>, LBboundary.h:109-160:
+    the same beta / gamma / delta pairs as the bounce-back helper, isSolid being !isFluid), as the argument of
+    Lattice.add_constant_links: node_q [n, 2] = (grid.neighbor(q, node), q) in the reference's store order, and the
+    stored values -- w[q] * rho_bnd[node, field_no], or rho * w[q] * (1 + c2Inv cu + c4Inv0_5 (cu^2 - c2 u^2))."""
+    lattice = tab.g.lattice
+    w = lattice_weights(lattice)
+    nodes, n_beta, n_gamma, n_delta, links = tab.halfway_bb(np.asarray(bnd_nodes, dtype=np.int32))
+    nd = 2 if lattice == "D2Q9" else 3
+    v = [float(x) for x in list(vel)[:nd]]
+    u_sq = v[0] * v[0] + v[1] * v[1]
+    if nd == 3:
+        u_sq = u_sq + v[2] * v[2]
+    cu = _c_dot_all(lattice, v)
+    c2inv, c4inv0_5, c2 = 3.0, 4.5, 1.0 / 3.0
+
+    def value(q, node):
+        if kind == "pressure":
+            return w[q] * float(rho_bnd[node, field_no])
+        return rho * w[q] * (1.0 + c2inv * cu[q] + c4inv0_5 * (cu[q] * cu[q] - c2 * u_sq))
+
+    node_q, values = [], []
+    for b, node in enumerate(nodes):
+        for q in links[b, :n_beta[b]]:
+            node_q.append((int(tab.neigh[node, q]), int(q)))
+            values.append(value(q, node))
+        for q in links[b, n_beta[b] + n_gamma[b]:n_beta[b] + n_gamma[b] + n_delta[b]]:
+            r = G.reverse_direction(lattice, int(q))
+            node_q.append((int(tab.neigh[node, q]), int(q)))
+            values.append(value(q, node))
+            node_q.append((int(tab.neigh[node, r]), r))
+            values.append(value(r, node))
+    return np.array(node_q, dtype=np.int32).reshape(-1, 2), np.array(values, dtype=np.float64)

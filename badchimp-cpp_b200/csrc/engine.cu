@@ -45,6 +45,7 @@ int buildPeerTables(chimp_lattice *c);
 int buildPhiExceptions(chimp_lattice *c);
 int checkDeviceError(chimp_lattice *c);
 void awaitPeers(chimp_lattice *c);
+void restoreConstants(chimp_lattice *c, double *X);
 std::atomic<long long> g_launches{0};
 
 int fail(const char *fmt, ...)
@@ -80,7 +81,7 @@ int revDir(const LatInfo &li, int q) { return q == li.nQ - 1 ? q : (q + li.nPair
 struct MailSlot { double value; unsigned long long seq; };
 constexpr int kMaxWorld = 64;
 
-struct Op { int kind, dn, dq, sn, sq; }; // kind 0 copy, 1 anti bounce back, 2 swap
+struct Op { int kind, dn, dq, sn, sq; }; // kind 0 copy, 1 anti bounce back, 2 swap, 3 constant (sn = index of the value)
 
 struct Neighbor {
     int rank = -1;
@@ -128,6 +129,13 @@ struct chimp_lattice {
     int nNodes = 0;
     std::vector<int32_t> neigh, bulk;
     std::vector<Op> ops;
+    // constant links (PressureBnd / InletOutlet, LBpressurebnd.h:10-88): values by registration order, the halo-in slot each
+    // one occupies (offset inside one field's planes), and their device copies
+    std::vector<double> constValues;
+    std::vector<long long> hConstDst;
+    double *d_constVal = nullptr;
+    long long *d_constDst = nullptr;
+    bool constDirty = false; // the buffer read next holds uploaded / initial values in the constant links' slots
     std::vector<Neighbor> nbrs;
     std::vector<int32_t> solidBnd;
     bool finalized = false, hostBuilt = false;
@@ -205,6 +213,16 @@ struct chimp_lattice {
 };
 
 namespace {
+
+// the constant links' slots of buffer X take their values again (after anything that wrote whole planes or
+// scattered a state through the pull table); stream-ordered on the engine's stream
+void restoreConstants(chimp_lattice *c, double *X)
+{
+    const long long n = (long long)c->hConstDst.size();
+    if (!n || !c->d_constDst) return;
+    haloUnpackKernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(X, c->d_constVal, c->d_constDst, (int)n);
+    ++g_launches;
+}
 
 int check(chimp_lattice *c, bool needFinal)
 {
@@ -504,6 +522,20 @@ int chimp_add_links(chimp_lattice *c, int kind, int n_links, const int32_t *l4)
     return 0;
 }
 
+int chimp_add_constant_links(chimp_lattice *c, int n_links, const int32_t *node_q, const double *values)
+{
+    if (check(c, false)) return 1;
+    if (c->nFields != 1) return fail("constant links need a one-field lattice (both fields of a two-field lattice share the pull table)");
+    if (n_links < 0 || (n_links > 0 && (!node_q || !values))) return fail("bad constant-link arguments");
+    for (int k = 0; k < n_links; ++k) {
+        const int node = node_q[2 * k], q = node_q[2 * k + 1];
+        if (node < 0 || node >= c->nNodes || q < 0 || q >= c->li.nQ) return fail("constant link %d: node %d / direction %d out of range", k, node, q);
+        c->ops.push_back({3, node, q, (int)c->constValues.size(), 0});
+        c->constValues.push_back(values[k]);
+    }
+    return 0;
+}
+
 int chimp_add_neighbor(chimp_lattice *c, int neig_rank, int n_send, const int32_t *nodes_to_send,
                        const int32_t *n_dir_send, const int32_t *dir_list_send, int n_recv,
                        const int32_t *nodes_received, const int32_t *n_dir_recv, const int32_t *dir_list_recv)
@@ -598,6 +630,7 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
     }
     // 3. boundary copies in application order
     std::vector<uint32_t> pmaskB(nBulk, 0);
+    std::vector<std::pair<long long, int>> constElem; // (halo element, index of its value)
     auto orient = [&](int32_t code, int sq, int dq, int32_t &outCode) -> bool {
         if (code == UNSET || code == POISON) { outCode = code; return true; }
         if (code <= -2) { outCode = sq == dq ? code : POISON; return true; }
@@ -610,7 +643,14 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
     for (const Op &op : c->ops) {
         const size_t d = (size_t)op.dn * nQ + op.dq, s = (size_t)op.sn * nQ + op.sq;
         int32_t v;
-        if (op.kind == 0) {
+        if (op.kind == 3) {
+            // the destination takes a constant: a halo-in element nobody sends to, filled once by the engine
+            sym[d] = (int32_t)(-2 - haloTotal);
+            haloQH.push_back({op.dq, haloDirCount[0][op.dq]++});
+            constElem.push_back({haloTotal, op.sn});
+            ++haloTotal;
+            if (haloTotal > (1ll << 30)) return fail("halo too large");
+        } else if (op.kind == 0) {
             if (!orient(sym[s], op.sq, op.dq, v)) return fail("boundary copy (%d,%d)<-(%d,%d): unsupported direction change", op.dn, op.dq, op.sn, op.sq);
             sym[d] = v;
         } else if (op.kind == 1) {
@@ -707,6 +747,11 @@ int chimp_build_host(chimp_lattice *c, int boundary_first)
             dst[e] = (long long)qh.first * c->stride + c->nPad + qh.second;
         }
         haloOff += nb.recvCount;
+    }
+    c->hConstDst.assign(c->constValues.size(), -1);
+    for (const auto &ce : constElem) {
+        const auto &qh = haloQH[(size_t)ce.first];
+        c->hConstDst[(size_t)ce.second] = (long long)qh.first * c->stride + c->nPad + qh.second;
     }
     if (c->nFields == 2) {
         // phi slots: own nodes, solid-boundary nodes, ghost nodes (in neighbour / list order), one zero slot
@@ -822,6 +867,17 @@ int chimp_finalize(chimp_lattice *c, int index_form, int boundary_first)
     if (index_form == CHIMP_INDEX_COMPACT && buildRankIndex(c)) return 1;
     if (index_form == CHIMP_INDEX_TABLE && buildKernelTable(c)) return 1;
     if (allocateState(c)) return 1;
+    if (!c->hConstDst.empty()) {
+        for (long long d : c->hConstDst)
+            if (d < 0) return fail("internal error: a constant link has no slot");
+        CUDA_OK(cudaMalloc(&c->d_constVal, c->constValues.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(c->d_constVal, c->constValues.data(), c->constValues.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->d_constDst, c->hConstDst.size() * sizeof(long long)));
+        CUDA_OK(cudaMemcpy(c->d_constDst, c->hConstDst.data(), c->hConstDst.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        restoreConstants(c, c->d_f[0]);
+        restoreConstants(c, c->d_f[1]);
+        CUDA_OK(cudaGetLastError());
+    }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     if (labelRangeOf(c)) return 1; // row range of the host arrays, so that the first transfer does not pay for it
     if (c->d_ptable && buildPhiExceptions(c)) return 1;
@@ -889,6 +945,7 @@ void chimp_destroy(chimp_lattice *c)
     if (c->h_error) cudaFreeHost(c->h_error);
     freeDev(c->d_ptable); freeDev(c->d_phi); freeDev(c->d_fluxPartial); freeDev(c->d_fluxSum); freeDev(c->d_forceX);
     freeDev(c->d_excInfo); freeDev(c->d_exc);
+    freeDev(c->d_constVal); freeDev(c->d_constDst);
     freeDev(c->d_forceOn); freeDev(c->d_addSource); freeDev(c->d_srcPerLabel); freeDev(c->d_massPartial);
     freeDev(c->d_labelAttr); freeDev(c->d_scale); freeDev(c->d_mass);
     for (auto &nb : c->nbrs) {
@@ -941,8 +998,9 @@ struct Staging {
 static int acquireStaging(chimp_lattice *c, size_t bytes, Staging &st)
 {
     const size_t have = (size_t)c->nFields * c->li.nQ * (size_t)c->stride * sizeof(double);
-    // not with peer halos: the neighbours may already be storing the next step's populations into that buffer
-    if (bytes <= have && !c->peerHalos) {
+    // not with peer halos: the neighbours may already be storing the next step's populations into that buffer;
+    // not with constant links: their slots of that buffer keep their values from finalize on
+    if (bytes <= have && !c->peerHalos && c->hConstDst.empty()) {
         st.ptr = c->d_f[c->cur ^ 1];
         return 0;
     }
@@ -974,6 +1032,7 @@ int chimp_upload_lbfield(chimp_lattice *c, const double *f_aos)
     case CHIMP_D3Q27: scatterStateKernel<D3Q27><<<grid, 256, 0, c->stream>>>(shifted, X, c->d_table, c->d_label, c->n, c->nPad, c->stride, c->nFields); break;
     }
     ++g_launches;
+    c->constDirty = !c->hConstDst.empty(); // the constant links' slots hold uploaded values until the first step has read them
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return checkDeviceError(c);
@@ -1283,6 +1342,13 @@ int stepEnd(chimp_lattice *c)
         CUDA_OK(cudaEventRecord(c->evHalo, c->haloStream));
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
     }
+    if (c->constDirty) {
+        // An upload or initialisation put ordinary values into the constant links' slots of the buffer this step has
+        // read -- the reference's field before the first apply() (LBpressurebnd.h:19-41).  From now on they hold the
+        // constants again (the other buffer's were never touched).
+        restoreConstants(c, c->d_f[c->cur]);
+        c->constDirty = false;
+    }
     c->cur ^= 1;
     ++c->steps;
     return 0;
@@ -1384,6 +1450,7 @@ int chimp_init_uniform(chimp_lattice *c, double rho)
             fillKernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(c->d_f[c->cur] + ((long long)f * c->li.nQ + q) * c->stride, wq[q], count);
             ++g_launches;
         }
+    c->constDirty = !c->hConstDst.empty();
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -1403,6 +1470,7 @@ int chimp_init_equilibrium_dev(chimp_lattice *c, const double *rho_dev)
     case CHIMP_D3Q27: initEquilibriumKernel<D3Q27><<<grid, 256, 0, c->stream>>>(rho_dev, X, c->d_table, c->n, c->nPad, c->stride, c->nFields); break;
     }
     ++g_launches;
+    c->constDirty = !c->hConstDst.empty();
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;

@@ -1,7 +1,10 @@
 // std_case on the B200 engine: the structure of the reference's src/std_case/main.cpp:17-160 with
 // the per-node loop, swapData, communicateLbField and bounceBackBnd.apply replaced by one call.
 //
-//   std_case <lattice D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess [vtk dir]]
+//   std_case <lattice D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess [vtk dir|- [pressure|inletoutlet]]]
+//
+// The last argument adds the library's PressureBnd / InletOutlet (LBpressurebnd.h) on every third fluid boundary node,
+// with the prescribed values of oracle/ref_driver --pressure-bnd (tests/test_library_bnd.py).
 //
 // Reads the same files as the reference main (input deck, <prefix><rank>.vtklb), runs
 // iterations/max iterations and writes raw f (LbField layout), rho and vel for the parity tests.
@@ -27,7 +30,8 @@ struct Rank {
 };
 
 template <typename LT>
-int run(const std::string &inputFile, const std::string &prefix, int firstRank, const std::string &outFile, int nRanks, const std::string &vtkDir)
+int run(const std::string &inputFile, const std::string &prefix, int firstRank, const std::string &outFile, int nRanks, const std::string &vtkDir,
+        const std::string &libraryBnd)
 {
     Input input(inputFile);
     const int nIterations = input["iterations"]["max"];
@@ -59,6 +63,21 @@ int run(const std::string &inputFile, const std::string &prefix, int firstRank, 
         R.gpu.reset(new GpuLattice<LT>(*R.grid, R.bulkNodes, 1));
         R.gpu->add(*R.mpiBoundary);
         R.gpu->add(bounceBackBnd);
+        if (!libraryBnd.empty()) {
+            const std::vector<int> fluidBnd = findFluidBndNodes(*R.nodes);
+            std::vector<int> bndNodes;
+            for (std::size_t k = 0; k < fluidBnd.size(); k += 3) bndNodes.push_back(fluidBnd[k]);
+            if (libraryBnd == "pressure") {
+                ScalarField rhoBnd(1, R.grid->size());
+                for (int n = 0; n < R.grid->size(); ++n) rhoBnd(0, n) = 1.0 + 0.01 * (n % 7);
+                PressureBnd<LT> pressureBnd(bndNodes, *R.nodes, *R.grid);
+                R.gpu->add(pressureBnd, 0, *R.grid, rhoBnd);
+            } else {
+                const std::vector<lbBase_t> v{0.01, -0.005, 0.002};
+                InletOutlet<LT> inletOutlet(bndNodes, *R.nodes, *R.grid);
+                R.gpu->add(inletOutlet, *R.grid, 1.02, std::vector<lbBase_t>(v.begin(), v.begin() + LT::nD));
+            }
+        }
         R.gpu->finalize();
         R.gpu->upload(*R.f);
     }
@@ -124,15 +143,16 @@ int run(const std::string &inputFile, const std::string &prefix, int firstRank, 
 int main(int argc, char **argv)
 {
     if (argc < 6) {
-        std::cout << "usage: std_case <D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess [vtk output dir]]" << std::endl;
+        std::cout << "usage: std_case <D2Q9|D3Q19|D3Q27> <input.dat> <vtklb prefix> <rank> <out.bin> [nRanksInProcess [vtk output dir|- [pressure|inletoutlet]]]" << std::endl;
         return 2;
     }
     const std::string lattice = argv[1];
     const int rank = std::atoi(argv[4]);
     const int nRanks = argc > 6 ? std::atoi(argv[6]) : 1;
-    const std::string vtkDir = argc > 7 ? argv[7] : "";
-    if (lattice == "D2Q9") return run<D2Q9>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
-    if (lattice == "D3Q19") return run<D3Q19>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
-    if (lattice == "D3Q27") return run<D3Q27>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir);
+    const std::string vtkDir = argc > 7 && std::string(argv[7]) != "-" ? argv[7] : "";
+    const std::string libraryBnd = argc > 8 ? argv[8] : "";
+    if (lattice == "D2Q9") return run<D2Q9>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir, libraryBnd);
+    if (lattice == "D3Q19") return run<D3Q19>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir, libraryBnd);
+    if (lattice == "D3Q27") return run<D3Q27>(argv[2], argv[3], rank, argv[5], nRanks, vtkDir, libraryBnd);
     chimp_host::die("unknown lattice " + lattice);
 }

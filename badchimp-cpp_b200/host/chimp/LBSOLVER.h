@@ -7,6 +7,7 @@
 #include "LBvtk.h"
 #include "LBgrid.h"
 #include "LBhalfwaybb.h"
+#include "LBpressurebnd.h"
 #include "LBbndmpi.h"
 #include "LBcollision.h"
 #include "LBgpu.h"

@@ -59,6 +59,21 @@ public:
         chimpCheck(chimp_add_halfway_bb(h_, bb.size(), bb.nodeList().data(), bb.nBetaList().data(), bb.nGammaList().data(),
                                         bb.nDeltaList().data(), bb.linkList().data()));
     }
+    // PressureBnd / InletOutlet (LBpressurebnd.h): add them after the bounce back, in the order the main applies them
+    void add(const PressureBnd<DXQY> &bnd, int fieldNo, const Grid<DXQY> &grid, const ScalarField &rho)
+    {
+        std::vector<int> nodeQ;
+        std::vector<lbBase_t> values;
+        bnd.links(fieldNo, grid, rho, nodeQ, values);
+        chimpCheck(chimp_add_constant_links(h_, int(values.size()), nodeQ.data(), values.data()));
+    }
+    void add(const InletOutlet<DXQY> &bnd, const Grid<DXQY> &grid, const lbBase_t &rho, const std::vector<lbBase_t> &vel)
+    {
+        std::vector<int> nodeQ;
+        std::vector<lbBase_t> values;
+        bnd.links(grid, rho, vel, nodeQ, values);
+        chimpCheck(chimp_add_constant_links(h_, int(values.size()), nodeQ.data(), values.data()));
+    }
     void add(const BndMpi<DXQY> &mpi)
     {
         for (const MonLatLists &m : mpi.lists())

@@ -66,6 +66,15 @@ int chimp_add_halfway_bb(chimp_lattice *, int n_bnd, const int32_t *nodes, const
  * after streaming in the order added (main.cpp:591-597). */
 int chimp_add_links(chimp_lattice *, int kind, int n_links, const int32_t *links4);
 
+/* PressureBnd<DXQY>::apply / InletOutlet<DXQY>::apply (LBpressurebnd.h:10-88): after the boundary phase of every step the
+ * population f(q_k, node_k) holds value_k.  node_q = n_links pairs (destination node label, direction); for the
+ * reference classes the destination is grid.neighbor(beta, bndNode) with value w[beta] * rho(bndNode)  (PressureBnd) or
+ * rho * w[beta] * (1 + c2Inv cu + c4Inv0_5 (cu^2 - c2 u^2))  (InletOutlet); the host mirror host/chimp/LBpressurebnd.h
+ * forms exactly those products.  The values are captured here (a prescribed density / velocity; the reference has no
+ * caller that varies them).  Call in the order the main applies its boundaries, before chimp_finalize; one-field
+ * lattices only.  Downloads return the constants at those places, like the reference's field after apply(). */
+int chimp_add_constant_links(chimp_lattice *, int n_links, const int32_t *node_q, const double *values);
+
 /* one MonLatMpi (LBmonlatmpi.h:72-98): ghost exchange lists towards one neighbour rank, in
  * the reference's list order.  Neighbours must be added in ascending rank order (LBvtk.h:534-544). */
 int chimp_add_neighbor(chimp_lattice *, int neig_rank, int n_send, const int32_t *nodes_to_send,

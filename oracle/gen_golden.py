@@ -59,6 +59,8 @@ def run_reference(name, geo, lattice, periodic, case, steps, dump, args, attribu
     subprocess.run(cmd, check=True, capture_output=True)
     gold = {"geo": np.asarray(geo, dtype=np.int32), "lattice": lattice, "periodic": periodic, "case": case,
             "steps": steps, "dump": np.array(dump), "args": np.array([str(a) for a in args]), "nranks": nranks}
+    if any(str(e).startswith("--pressure-bnd") for e in extra):
+        gold["extra"] = np.array([str(e) for e in extra])
     for aname, aval in attributes.items():
         gold["attr." + aname] = np.asarray(aval)
     for r in range(nranks):
@@ -152,17 +154,38 @@ def restart_and_forcing_goldens():
                   extra=["--no-tables", "--no-f", "--global-forcing", "--fixed-flux", "2e-5", "--cap-numb", "1e-4,0.1666666666666666574,0.1"])
 
 
+def library_bnd_goldens():
+    """round 2: the reference's own PressureBnd / InletOutlet classes (LBpressurebnd.h:10-88; no caller in its mains)
+    applied after the bounce back of every std_case step on every third fluid boundary node (ref_driver --pressure-bnd)"""
+    shape = (12, 10, 14)
+    pack = G.sphere_pack(shape, 3.2, 0.62, 11).astype(int)
+    ones = np.ones(shape)
+    F3 = "--force", "1e-6,2e-7,-3e-7"
+    run_reference("pbnd_d3q19_p1", pack, "D3Q19", "xyz", "std_case", 6, [1, 2, 6], ["--tau", 0.8, *F3], {"init_rho": ones},
+                  extra=["--pressure-bnd", "pressure", "--bnd-every", "3"])
+    run_reference("inout_d3q19_p2", G.z_slab_rank_map(pack, 2), "D3Q19", "xyz", "std_case", 6, [1, 6], ["--tau", 0.8, *F3], {"init_rho": ones},
+                  extra=["--pressure-bnd", "inletoutlet", "--bnd-every", "3", "--io-rho", "1.02", "--io-vel", "0.01,-0.005,0.002"])
+    pack2 = G.sphere_pack((16, 12), 2.5, 0.7, 5).astype(int)
+    run_reference("inout_d2q9_p1", pack2, "D2Q9", "xy", "std_case", 8, [1, 8], ["--tau", 0.7, "--force", "1e-6,-2e-6,0"],
+                  {"init_rho": np.ones(pack2.shape)},
+                  extra=["--pressure-bnd", "inletoutlet", "--bnd-every", "2", "--io-rho", "0.98", "--io-vel", "0.02,0.01,0"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
     if sys.argv[1:] == ["vtk"]:
         vtk_goldens()
         return
+    if sys.argv[1:] == ["library-bnd"]:
+        library_bnd_goldens()
+        return
     if sys.argv[1:] == ["round2"]:
         restart_and_forcing_goldens()
         return
     vtk_goldens()
     restart_and_forcing_goldens()
+    library_bnd_goldens()
     shape = (12, 10, 14)
     pack = G.sphere_pack(shape, 3.2, 0.62, 11).astype(int)
     ones = np.ones(shape)

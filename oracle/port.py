@@ -74,7 +74,35 @@ class PortRank:
                        len(self.bb[0]), _p(self.bb[0]), _p(self.bb[1]), _p(self.bb[2]), _p(self.bb[3]), _p(self.bb[4]))
         return t
 
+    def set_library_bnd(self, kind, lists, rho_bnd=None, rho=1.0, vel=(0.0, 0.0, 0.0)):
+        """PressureBnd ("pressure": rho_bnd[n_nodes, n_fields]) or InletOutlet ("inletoutlet": rho, vel) of
+        LBpressurebnd.h:10-88 on the boundary nodes of `lists` (nodes, nBeta, nGamma, nDelta, links), applied after
+        the bounce back of every std_case step"""
+        self.lib_bnd = (kind, [_i32(x) for x in lists], None if rho_bnd is None else _f64(rho_bnd), float(rho),
+                        _f64(list(vel) + [0.0] * (3 - len(vel))))
+
+    def apply_library_bnd(self, fld=0):
+        kind, l, rho_bnd, rho, vel = self.lib_bnd
+        t = self.tables()
+        if kind == "pressure":
+            lib().port_pressure_bnd_apply(C.byref(t), _p(self.f), C.c_int(fld), C.c_int(len(l[0])), _p(l[0]), _p(l[1]), _p(l[2]),
+                                          _p(l[3]), _p(l[4]), _p(rho_bnd))
+        else:
+            lib().port_inlet_outlet_apply(C.byref(t), _p(self.f), C.c_int(fld), C.c_int(len(l[0])), _p(l[0]), _p(l[1]), _p(l[2]),
+                                          _p(l[3]), _p(l[4]), C.c_double(rho), _p(vel))
+
     def step_std_case(self, n_steps, tau=0.8, force=(0, 0, 0), trt=None, skip_boundary=False):
+        if getattr(self, "lib_bnd", None) is not None and not skip_boundary:
+            bnd, self.lib_bnd = self.lib_bnd, None
+            try:
+                for _ in range(n_steps):    # the library boundary follows the bounce back of every step
+                    self.step_std_case(1, tau, force, trt)
+                    self.lib_bnd = bnd
+                    self.apply_library_bnd()
+                    self.lib_bnd = None
+            finally:
+                self.lib_bnd = bnd
+            return
         F = _f64(list(force) + [0.0] * (3 - len(force)))
         ts, ta = trt if trt else (0.0, 0.0)
         t = self.tables()

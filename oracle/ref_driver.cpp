@@ -47,6 +47,7 @@
 #include "lbsolver/LBnodes.h"
 #include "lbsolver/LBgeometry.h"
 #include "lbsolver/LBhalfwaybb.h"
+#include "lbsolver/LBpressurebnd.h"
 #include "lbsolver/LBmacroscopic.h"
 #include "lbsolver/LBcollision.h"
 #include "lbsolver/LBcollision2phase.h"
@@ -75,6 +76,12 @@ struct Opts {
     std::vector<double> force{0, 0, 0};
     double tau0 = 1, tau1 = 1, sigma = 0.01, beta = 1, momx = 1e-5; // twophase
     double rhoW = 1.0;                                             // one_phase pressure bnd
+    // std_case: the reference's own PressureBnd / InletOutlet (LBpressurebnd.h:10-88) applied after the bounce back on
+    // every `bndEvery`-th fluid boundary node: "pressure" (rho of node n prescribed as 1 + 0.01 (n % 7)) or "inletoutlet"
+    std::string pressureBnd;
+    int bndEvery = 3;
+    double ioRho = 1.02;
+    std::vector<double> ioVel{0.01, -0.005, 0.002};
 };
 
 class RecFile
@@ -215,6 +222,30 @@ double runStdCase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid,
         for (int d = 0; d < LT::nD; ++d) vel(0, d, n) = 0.0;
     HalfWayBounceBack<LT> bb(findFluidBndNodes(nodes), nodes, grid);
     if (o.dumpTables) dumpBounceBack(rec, "bb.", bb);
+    // library pressure boundaries (no caller in the reference's mains; exercised here through their own classes)
+    std::vector<int> pbNodes;
+    if (!o.pressureBnd.empty()) {
+        const std::vector<int> fb = findFluidBndNodes(nodes);
+        for (std::size_t k = 0; k < fb.size(); k += (std::size_t)o.bndEvery) pbNodes.push_back(fb[k]);
+    }
+    PressureBnd<LT> pressureBnd(pbNodes, nodes, grid);
+    InletOutlet<LT> inletOutlet(pbNodes, nodes, grid);
+    ScalarField rhoBnd(1, sz);
+    for (int n = 0; n < sz; ++n) rhoBnd(0, n) = 1.0 + 0.01 * (n % 7);
+    const std::vector<lbBase_t> ioVel(o.ioVel.begin(), o.ioVel.begin() + LT::nD);
+    if (!o.pressureBnd.empty()) {
+        rec.ints("pbnd.nodes", pbNodes);
+        std::vector<int> nb, nd, links;
+        for (int b = 0; b < pressureBnd.size(); ++b) {
+            nb.push_back((int)pressureBnd.beta(b).size());
+            nd.push_back((int)pressureBnd.delta(b).size());
+            for (int q : pressureBnd.beta(b)) links.push_back(q);
+            for (int q : pressureBnd.delta(b)) links.push_back(q);
+        }
+        rec.ints("pbnd.nBeta", nb);
+        rec.ints("pbnd.nDelta", nd);
+        rec.ints("pbnd.links", links);
+    }
     LbField<LT> f(1, sz), fTmp(1, sz);
     for (auto n : bulk)
         for (int q = 0; q < LT::nQ; ++q) f(0, q, n) = LT::w[q] * rho(0, n);
@@ -269,6 +300,8 @@ double runStdCase(const Opts &o, RecFile &rec, LBvtk<LT> &vtklb, Grid<LT> &grid,
         f.swapData(fTmp);
         mpi.communicateLbField(0, f, grid);
         bb.apply(f, grid);
+        if (o.pressureBnd == "pressure") pressureBnd.apply(0, f, grid, rhoBnd);        // LBpressurebnd.h:19-41
+        else if (o.pressureBnd == "inletoutlet") inletOutlet.apply(0, f, grid, o.ioRho, ioVel); // LBpressurebnd.h:51-88
         dump(i);
     }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -675,6 +708,10 @@ int main(int argc, char **argv)
         else if (a == "--beta") o.beta = std::stod(next());
         else if (a == "--momx") o.momx = std::stod(next());
         else if (a == "--rhow") o.rhoW = std::stod(next());
+        else if (a == "--pressure-bnd") o.pressureBnd = next();
+        else if (a == "--bnd-every") o.bndEvery = std::max(1, std::stoi(next()));
+        else if (a == "--io-rho") o.ioRho = std::stod(next());
+        else if (a == "--io-vel") { auto v = parseList(next()); v.resize(3, 0.0); o.ioVel = v; }
         else { std::cerr << "unknown option " << a << std::endl; return 1; }
     }
     mpishim::init(o.nranks);

@@ -74,8 +74,9 @@ class Golden:
 
 def all_golden_names():
     """goldens that carry the reference's integer tables and field dumps (the round-2 restart_* / forcing_* goldens hold
-    field dumps or function values only and have their own tests, tests/test_restart_and_forcing.py)"""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("restart_", "forcing_")))
+    field dumps or function values only and have their own tests, tests/test_restart_and_forcing.py; the pbnd_* / inout_*
+    goldens run the reference's library pressure boundaries on top of std_case, tests/test_library_bnd.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("restart_", "forcing_", "pbnd_", "inout_")))
 
 
 def build_tables(g: Golden):
