@@ -16,6 +16,7 @@
 #include "LBnodes.h"
 #include "LBfield.h"
 #include "LBhalfwaybb.h"
+#include "LBpressurebnd.h"
 
 template <typename DXQY> struct ChimpLatticeId;
 template <> struct ChimpLatticeId<D2Q9>  { static constexpr int value = CHIMP_D2Q9;  };
@@ -49,6 +50,37 @@ public:
             for (auto q : bb.delta(n)) links.push_back(q);
         }
         chimpCheck(chimp_add_halfway_bb(h_, bb.size(), node.data(), nb.data(), ng.data(), nd.data(), links.data()));
+    }
+    // PressureBnd<DXQY> bnd(bndNodes, nodes, grid);  ->  gpu.add(bnd, fieldNo, grid, rho);   replaces bnd.apply(fieldNo, f, grid, rho)
+    // (LBpressurebnd.h:19-41).  Same stores in the same order; the densities are taken now (a prescribed boundary density).
+    void add(const PressureBnd<DXQY> &bnd, int fieldNo, const Grid<DXQY> &grid, const ScalarField &rho) {
+        std::vector<int32_t> nodeQ;
+        std::vector<lbBase_t> values;
+        auto store = [&](int q, int nodeNo) {
+            nodeQ.push_back(grid.neighbor(q, nodeNo)); nodeQ.push_back(q);
+            values.push_back(DXQY::w[q] * rho(fieldNo, nodeNo));
+        };
+        for (int n = 0; n < bnd.size(); ++n) {
+            for (auto beta : bnd.beta(n)) store(beta, bnd.nodeNo(n));
+            for (auto delta : bnd.delta(n)) { store(delta, bnd.nodeNo(n)); store(bnd.dirRev(delta), bnd.nodeNo(n)); }
+        }
+        chimpCheck(chimp_add_constant_links(h_, int(values.size()), nodeQ.data(), values.data()));
+    }
+    // InletOutlet<DXQY> bnd(...);  ->  gpu.add(bnd, grid, rho, vel);   replaces bnd.apply(fieldNo, f, grid, rho, vel)  (:51-88)
+    void add(const InletOutlet<DXQY> &bnd, const Grid<DXQY> &grid, const lbBase_t &rho, const std::vector<lbBase_t> vel) {
+        std::vector<int32_t> nodeQ;
+        std::vector<lbBase_t> values;
+        lbBase_t u_sq = DXQY::dot(vel, vel);
+        std::valarray<lbBase_t> cu = DXQY::cDotAll(vel);
+        auto store = [&](int q, int nodeNo) {
+            nodeQ.push_back(grid.neighbor(q, nodeNo)); nodeQ.push_back(q);
+            values.push_back(rho * DXQY::w[q] * (1.0 + DXQY::c2Inv * cu[q] + DXQY::c4Inv0_5 * (cu[q] * cu[q] - DXQY::c2 * u_sq)));
+        };
+        for (int n = 0; n < bnd.size(); ++n) {
+            for (auto beta : bnd.beta(n)) store(beta, bnd.nodeNo(n));
+            for (auto delta : bnd.delta(n)) { store(delta, bnd.nodeNo(n)); store(bnd.dirRev(delta), bnd.nodeNo(n)); }
+        }
+        chimpCheck(chimp_add_constant_links(h_, int(values.size()), nodeQ.data(), values.data()));
     }
     // std_one_phase: auto solidFluidLinks = findSolidFluidLinks(nodes, grid);  ->  gpu.addLinks(CHIMP_LINK_SOLID, links)
     void addLinks(int kind, const std::vector<std::vector<int>> &l) {

@@ -9,7 +9,10 @@
 // as raw records so that tests/test_integration_stub.py can compare them with the golden dump of the reference's
 // own CPU loop (tests/golden/std_d3q19_p1.npz).
 //
-//   integration_std_case <dir with tmp0.vtklb> <output dir> <nIterations> <nItrWrite> <tau> <Fx> <Fy> <Fz>
+//   integration_std_case <dir with tmp0.vtklb> <output dir> <nIterations> <nItrWrite> <tau> <Fx> <Fy> <Fz> [pressure|inletoutlet]
+//
+// The optional last argument adds the reference's own PressureBnd / InletOutlet object (LBpressurebnd.h; no main of
+// the reference uses them) on every third fluid boundary node, with the prescribed values of ref_driver --pressure-bnd.
 #include "LBSOLVER.h"
 #include "IO.h"
 #include "LBgpu.h"
@@ -82,6 +85,20 @@ int main(int argc, char **argv)
     // ---- new: the engine takes over the node loop (replaces main.cpp:110-145)
     GpuLattice<LT> gpu(grid, bulkNodes, 1);
     gpu.add(bounceBackBnd);                          // replaces bounceBackBnd.apply(f, grid)
+    if (argc > 9) {
+        const std::vector<int> fluidBnd = findFluidBndNodes(nodes);
+        std::vector<int> bndNodes;
+        for (std::size_t k = 0; k < fluidBnd.size(); k += 3) bndNodes.push_back(fluidBnd[k]);
+        if (std::string(argv[9]) == "pressure") {
+            ScalarField rhoBnd(1, grid.size());
+            for (int n = 0; n < grid.size(); ++n) rhoBnd(0, n) = 1.0 + 0.01 * (n % 7);
+            PressureBnd<LT> pressureBnd(bndNodes, nodes, grid);
+            gpu.add(pressureBnd, 0, grid, rhoBnd);    // replaces pressureBnd.apply(0, f, grid, rhoBnd)
+        } else {
+            InletOutlet<LT> inletOutlet(bndNodes, nodes, grid);
+            gpu.add(inletOutlet, grid, 1.02, std::vector<lbBase_t>{0.01, -0.005, 0.002});
+        }
+    }
     gpu.finalize();
     gpu.upload(f);
 

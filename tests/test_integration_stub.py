@@ -116,3 +116,17 @@ def test_reference_one_phase_main_switched_to_the_engine(tmp_path):
     for n, ph in zip(setup["press_nodes"], setup["press_phase"]):
         want[ph] += ref_vel[n, 2] * ref_rho[n]
     assert np.allclose(rec[s + "massFlux"], want, rtol=1e-9, atol=1e-18)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(BINARY), reason="needs oracle/_ref/integration_std_case (built where the reference tree is)")
+def test_reference_pressure_bnd_object_handed_to_the_engine(tmp_path):
+    """the reference's OWN PressureBnd<D3Q19> object (LBpressurebnd.h:10-41; no main of the reference uses it) handed to
+    the binding stub's GpuLattice::add in the switched std_case main: the dumps of the reference's CPU loop with
+    pressureBnd.apply() after the bounce back (golden pbnd_d3q19_p1), bit for bit"""
+    g = helpers.Golden("pbnd_d3q19_p1")
+    F = g.force()
+    t, rec = _run_switched_main(BINARY, g, tmp_path, ["6", "4", repr(g.args["tau"]), repr(F[0]), repr(F[1]), repr(F[2]), "pressure"])
+    bulk = t.bulk_nodes()
+    assert np.array_equal(rec["step6.f"].reshape(-1, 19)[bulk], g.f(0, 6)[bulk, 0])
+    assert np.array_equal(rec["step6.rho"][bulk], g.rec(0, "step6.rho")[bulk])
