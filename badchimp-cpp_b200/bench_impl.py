@@ -23,6 +23,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B_ALG = {"D2Q9": 144.0, "D3Q19": 304.0, "D3Q27": 432.0}
+EXTRAS_BUDGET_S = 300.0   # default one-GPU run: wall-clock budget of the secondary workloads (later ones are skipped beyond it)
 
 
 def _peaks():
@@ -529,7 +530,7 @@ def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, p
         return e
 
     def guarded(name, fn):
-        if time.perf_counter() - t_begin > 300.0:
+        if time.perf_counter() - t_begin > EXTRAS_BUDGET_S:
             out.append({"workload_key": name, "skipped": "time budget of the default run used up"})
             return
         try:
@@ -559,7 +560,10 @@ def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, p
     except Exception:  # pragma: no cover
         pass
 
-    def fresh(name, interior=False):
+    def fresh(name, interior=False, ab=None):
+        """ab = (environment switch, key): the same workload is timed once more with that switch set to 0 -- the form
+        the default replaced (attribute arrays instead of the packed word, the full phi table instead of its derived
+        form) -- so that the line carries a measured A/B of the change"""
         def fn():
             wl = W.WORKLOADS[name]
             par = probe(name, wl, interior)
@@ -571,11 +575,31 @@ def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, p
                     e["mean_rho_error"] = abs(float(rho.mean()) - 1.0)
             finally:
                 rl.lat.close()
+            if ab and time.perf_counter() - t_begin < 0.8 * EXTRAS_BUDGET_S:
+                var, key = ab
+                saved = os.environ.get(var)
+                os.environ[var] = "0"      # read when a lattice is created
+                try:
+                    torch.cuda.empty_cache()
+                    rl2 = W.build(pkg, ingest, multi, wl, wl["size"], 0, 1, device, "strong", index_form, interior_domains=interior)
+                    try:
+                        e2 = timed_entry(name, rl2, wl)
+                        e[key] = {k: e2[k] for k in ("value", "ms_per_step", "phi_index_bytes_per_node", "attribute_bytes_per_node") if k in e2}
+                        e[key]["switch"] = var + "=0"
+                    finally:
+                        rl2.lat.close()
+                except Exception as exc:  # pragma: no cover -- the comparison is optional
+                    e[key] = {"error": str(exc)[:200]}
+                finally:
+                    if saved is None:
+                        os.environ.pop(var, None)
+                    else:
+                        os.environ[var] = saved
             return e
         return fn
-    guarded("one_phase", fresh("one_phase"))
+    guarded("one_phase", fresh("one_phase", ab=("CHIMP_ATTR_PACKED", "with_attribute_arrays")))
     guarded("one_phase+interior_domains", fresh("one_phase", True))
-    guarded("twophase", fresh("twophase"))
+    guarded("twophase", fresh("twophase", ab=("CHIMP_PHI_DERIVED", "with_phi_table")))
     guarded("d2q9_channel", fresh("d2q9_channel"))
     guarded("d3q27_dense", fresh("d3q27_dense"))
     return out
