@@ -84,7 +84,7 @@ class _Event:
 
 
 torch.cuda.is_available = lambda: True
-torch.cuda.device_count = lambda: 1
+torch.cuda.device_count = lambda: int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
 torch.cuda.current_device = lambda: 0
 torch.cuda.set_device = lambda d: None
 torch.cuda.synchronize = lambda *a, **k: _runtime().cudaDeviceSynchronize()
@@ -116,3 +116,32 @@ class _PatchedCDLL(_CDLL):
 
 
 ctypes.CDLL = _PatchedCDLL
+
+
+# N ranks as N processes (torchrun): the collectives run over gloo on CPU tensors; a collective "on a stream" first lets
+# every stream of this rank's model drain, which is the order NCCL would have had on that stream
+import torch.distributed as _dist  # noqa: E402
+
+_init_pg = _dist.init_process_group
+
+
+def _init_process_group(backend=None, *a, **k):
+    k.pop("device_id", None)
+    return _init_pg("gloo", *a, **k)
+
+
+_dist.init_process_group = _init_process_group
+
+
+def _drained(fn):
+    def wrapper(*a, **k):
+        _runtime().cudaDeviceSynchronize()
+        return fn(*a, **k)
+    wrapper.__name__ = getattr(fn, "__name__", "collective")
+    return wrapper
+
+
+for _name in ("all_reduce", "all_gather", "all_gather_object", "gather_object", "barrier", "batch_isend_irecv", "broadcast",
+              "send", "recv", "isend", "irecv"):
+    if hasattr(_dist, _name):
+        setattr(_dist, _name, _drained(getattr(_dist, _name)))

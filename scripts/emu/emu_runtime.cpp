@@ -7,8 +7,12 @@
 //   * streams and events execute at issue time; cudaMalloc is an aligned host allocation with red zones that
 //     cudaFree and the library destructor check
 #include "cuda_runtime.h"
+#include <fcntl.h>
 #include <sched.h>
+#include <sys/mman.h>
 #include <ucontext.h>
+#include <unistd.h>
+#include <atomic>
 #include <cstdio>
 #include <ctime>
 #include <condition_variable>
@@ -344,11 +348,44 @@ void enqueue(cudaStream_t stream, std::function<void()> op)
 }
 } // namespace emu
 
+// N processes as N ranks (torchrun + gloo): with CHIMP_EMU_ARENA=<file in /dev/shm> every process maps the same file at
+// the same address and cudaMalloc hands out pieces of it, so "device" pointers -- and with them the CUDA IPC handles,
+// which are the pointers themselves here -- mean the same memory in every rank, like peer-mapped GPU memory does.
+struct Arena {
+    std::atomic<size_t> offset;
+};
+Arena *g_arena = nullptr;
+constexpr size_t kArenaBytes = 48ull << 30;
+Arena *arena()
+{
+    static bool tried = false;
+    if (tried) return g_arena;
+    tried = true;
+    const char *path = getenv("CHIMP_EMU_ARENA");
+    if (!path || !*path) return nullptr;
+    const int fd = open(path, O_RDWR | O_CREAT, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)kArenaBytes) != 0) { perror("emu arena"); abort(); }
+    void *base = mmap((void *)0x6f0000000000ull, kArenaBytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED_NOREPLACE | MAP_NORESERVE, fd, 0);
+    close(fd);
+    if (base != (void *)0x6f0000000000ull) { perror("emu arena mmap"); abort(); }
+    g_arena = (Arena *)base;
+    size_t zero = 0;
+    g_arena->offset.compare_exchange_strong(zero, 4096); // the first process leaves room for this header
+    return g_arena;
+}
+
 extern "C" {
 cudaError_t cudaMalloc(void **p, size_t bytes)
 {
     const size_t padded = (bytes + 255) / 256 * 256;
-    unsigned char *raw = (unsigned char *)aligned_alloc(256, padded + 2 * kZone);
+    unsigned char *raw;
+    if (Arena *a = arena()) {
+        const size_t off = a->offset.fetch_add(padded + 2 * kZone);
+        if (off + padded + 2 * kZone > kArenaBytes) return cudaErrorMemoryAllocation;
+        raw = (unsigned char *)a + off;
+    } else {
+        raw = (unsigned char *)aligned_alloc(256, padded + 2 * kZone);
+    }
     if (!raw) return cudaErrorMemoryAllocation;
     memset(raw, kFill, padded + 2 * kZone); // fresh device memory is not zero: poison it (0xA5A5... is a huge negative double / int)
     *p = raw + kZone;
@@ -365,7 +402,7 @@ cudaError_t cudaFree(void *p)
     if (it == g_allocs.end()) { fprintf(stderr, "emu: cudaFree of unknown pointer %p\n", p); abort(); }
     if (!zonesIntact(p, it->second)) { fprintf(stderr, "emu: OUT-OF-BOUNDS WRITE next to allocation %p (%zu bytes)\n", p, it->second); abort(); }
     g_allocs.erase(it);
-    free((unsigned char *)p - kZone);
+    if (!g_arena) free((unsigned char *)p - kZone); // arena memory is not reused
     return cudaSuccess;
 }
 cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned) { *p = calloc(1, bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
@@ -385,9 +422,9 @@ cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, int kind, 
 }
 cudaError_t cudaMemset(void *dst, int v, size_t bytes) { if (bytes) memset(dst, v, bytes); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *dst, int v, size_t bytes, cudaStream_t s) { if (bytes) emu::enqueue(s, [dst, v, bytes]() { memset(dst, v, bytes); }); return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaSetDevice(int d) { return d >= 0 ? cudaSuccess : cudaErrorInvalidValue; } // every rank's "device" is the host
 cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { const char *w = getenv("LOCAL_WORLD_SIZE"); *n = w ? atoi(w) : 1; return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { drainAll(); return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { const int e = g_lastError; g_lastError = 0; return e; }
 const char *cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "emulated error"; }
