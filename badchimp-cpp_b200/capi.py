@@ -50,7 +50,7 @@ SYMBOLS = [
     "chimp_set_twophase_density", "chimp_step_twophase", "chimp_download_phase_field", "chimp_last_flux_force",
     "chimp_num_neighbors", "chimp_neighbor_info", "chimp_send_buffer_dev", "chimp_recv_buffer_dev",
     "chimp_set_exchange_callback", "chimp_set_stream", "chimp_synchronize", "chimp_num_own_nodes",
-    "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_irregular_fraction",
+    "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_host_constant_links", "chimp_irregular_fraction",
     "chimp_index_bytes_per_node", "chimp_phi_index_bytes_per_node", "chimp_one_phase_attribute_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_step_twophase_timed", "chimp_peer_mode", "chimp_voxel_table_host", "chimp_create_from_voxels",
     "chimp_voxel_phi_table_host", "chimp_set_phi_table_from_voxels", "chimp_slab_tables_host", "chimp_create_slab_from_voxels",
     "chimp_halo_face_recv_count", "chimp_halo_face_recv_list", "chimp_init_uniform",
@@ -201,6 +201,15 @@ class Lattice:
         dst = np.zeros(nr_f, dtype=np.int64)
         _check(lib().chimp_host_halo_lists(self.h, C.c_int(k), _p(src), _p(dst)))
         return rank.value, src, dst
+
+    def host_constant_links(self):
+        """(dst slot offsets q*stride + slot, values) of the constant links, in registration order"""
+        n = lib().chimp_host_constant_links(self.h, None, None)
+        if n < 0:
+            raise ChimpError(lib().chimp_last_error().decode())
+        dst, val = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.float64)
+        lib().chimp_host_constant_links(self.h, _p(dst), _p(val))
+        return dst, val
 
     def host_scalar_recv_slots(self, k):
         """ghost phi slots of neighbour k, in the order its values arrive"""

@@ -2907,6 +2907,14 @@ int chimp_host_halo_lists(chimp_lattice *c, int k, long long *send_src, long lon
     if (!c->hRecvDst[k].empty()) memcpy(recv_dst, c->hRecvDst[k].data(), c->hRecvDst[k].size() * sizeof(long long));
     return 0;
 }
+int chimp_host_constant_links(chimp_lattice *c, long long *dst, double *values)
+{
+    if (!c || !c->hostBuilt) { fail("host tables not built"); return -1; }
+    const size_t n = c->hConstDst.size();
+    if (dst && n) memcpy(dst, c->hConstDst.data(), n * sizeof(long long));
+    if (values && n) memcpy(values, c->constValues.data(), n * sizeof(double));
+    return (int)n;
+}
 int chimp_host_scalar_halo_lists(chimp_lattice *c, int k, long long *send_src, long long *recv_dst)
 {
     if (!c || !c->hostBuilt) return fail("host tables not built");

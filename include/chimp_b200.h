@@ -94,6 +94,9 @@ int chimp_build_host(chimp_lattice *, int boundary_first);
 int chimp_host_table_info(chimp_lattice *, long long *info6);
 int chimp_host_table(chimp_lattice *, int32_t *table, int32_t *labels, uint32_t *pmask);
 int chimp_host_halo_lists(chimp_lattice *, int k, long long *send_src, long long *recv_dst);
+/* the constant links (chimp_add_constant_links) in registration order: the slot offset q*plane_stride + slot each one
+ * occupies and its value; returns their number (either pointer may be null), -1 on error */
+int chimp_host_constant_links(chimp_lattice *, long long *dst, double *values);
 /* the same for the scalar (phi) halo of a two-field lattice: phi slots sent / ghost phi slots received */
 int chimp_host_scalar_halo_lists(chimp_lattice *, int k, long long *send_src, long long *recv_dst);
 

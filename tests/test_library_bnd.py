@@ -113,6 +113,75 @@ def test_link_values_are_the_ones_the_reference_stored(name):
         assert checked > 10
 
 
+@pytest.mark.parametrize("boundary_first", [False, True])
+@pytest.mark.parametrize("name", CASES)
+def test_pull_table_with_constant_links_reproduces_the_reference_step(name, boundary_first):
+    """No GPU: the pull table the engine's host builder makes of bounce back + library boundary (+ the 2-rank exchange),
+    evaluated in numpy over what the oracle port's nodes push in their second step, yields the field the reference holds
+    after that step's exchange, bounce back and apply() -- the constants sit in halo-in slots nobody sends to."""
+    g = helpers.Golden(name)
+    pkg = helpers.load_package()
+    kind, every, rho, vel = _options(g)
+    lg, tabs = helpers.build_tables(g)
+    port, ranks = _port_ranks(g, tabs)
+    exch = helpers.exchange_lists(tabs)
+    a = g.args
+
+    def full_step(skip_last_boundary):
+        for pr in ranks:
+            pr.step_std_case(1, tau=a["tau"], force=g.force(), skip_boundary=True)
+        if skip_last_boundary:
+            return
+        port.exchange_lb_field(ranks, exch, 0)
+        for pr in ranks:
+            pr.apply_bb(0)
+            pr.apply_library_bnd(0)
+
+    full_step(False)
+    full_step(True)                      # second step stopped after push + swap: pushed values sit in the neighbours' rows
+    nq = lg.nq
+    rev = np.array([pkg.geometry.reverse_direction(g.lattice, q) for q in range(nq)])
+    lats, X, tables = [], [], []
+    for t, pr in zip(tabs, ranks):
+        lat = pkg.capi.Lattice.from_rank_tables(t)
+        ss = t.send_side(tabs)
+        for k, nr in enumerate(t.neig_ranks):
+            lat.add_neighbor(nr, ss[k][0], ss[k][1], ss[k][2], t.recv_nodes[k], t.recv_ndir[k], t.recv_dirs[k])
+        lat.add_halfway_bb(*t.halfway_bb(t.fluid_bnd_nodes()))
+        node_q, values = pkg.cases.library_bnd_links(t, _bnd_nodes(t, every), kind, rho_bnd=_rho_bnd(t), rho=rho, vel=vel)
+        lat.add_constant_links(node_q, values)
+        lat.build_host(boundary_first)
+        table, labels, pmask, info = lat.host_table()
+        x = np.zeros((nq, info["stride"]))
+        for q in range(nq):
+            x[q, :info["n"]] = pr.f[t.neigh[labels, q], 0, q]
+        dst, val = lat.host_constant_links()
+        assert len(val) == len(values) and np.array_equal(val, values)
+        assert len(set(dst.tolist())) == len(dst) and (dst % info["stride"] >= info["n_pad"]).all()
+        x.ravel()[dst] = val
+        lats.append(lat); X.append(x); tables.append((table, labels, info))
+    packed = {}
+    for r, lat in enumerate(lats):
+        for k in range(lat.num_neighbors()):
+            nr, src, dst = lat.host_halo_lists(k)
+            packed[(r, nr)] = X[r].ravel()[src]
+    for r, lat in enumerate(lats):
+        for k in range(lat.num_neighbors()):
+            nr, src, dst = lat.host_halo_lists(k)
+            X[r].ravel()[dst] = packed[(nr, r)]
+    port.exchange_lb_field(ranks, exch, 0)
+    for pr in ranks:
+        pr.apply_bb(0)
+        pr.apply_library_bnd(0)
+    for r, pr in enumerate(ranks):
+        table, labels, info = tables[r]
+        i = np.arange(info["n"])
+        for q in range(nq):
+            src = table[q]
+            pulled = np.where(src >= 0, X[r][q, np.maximum(src, 0)], X[r][rev[q], i])
+            assert np.array_equal(pulled, pr.f[labels, 0, q]), "rank %d direction %d" % (r, q)
+
+
 def _engine_ranks(g, tabs, boundary_first):
     pkg = helpers.load_package()
     kind, every, rho, vel = _options(g)
