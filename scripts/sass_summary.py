@@ -11,6 +11,9 @@ LIB = os.path.join(ROOT, "badchimp-cpp_b200", "libchimp_b200.so")
 KERNELS = {
     "default single-GPU step kernel  collideStreamKernel<D3Q19, BGK, ONEPHASE=0, MOM=0, IDX_COMPACT, PEER=0>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELi0ELb0ELi1ELb0EEEvNS_8StepArgsE",
     "N-GPU step kernel (peer exchange fused)  collideStreamKernel<D3Q19, BGK, 0, 0, IDX_COMPACT, PEER=1>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELi0ELb0ELi1ELb1EEEvNS_8StepArgsE",
+    "one_phase step kernel, packed attribute word (untimed variant)  collideStreamKernel<D3Q19, TRT, OP_PACKED, 0, IDX_COMPACT, 0>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi1ELi2ELb0ELi1ELb0EEEvNS_8StepArgsE",
+    "two-phase collide pass, derived phi index (untimed variant)  twoPhaseCollideKernel<D3Q19, MOM=0, IDX_COMPACT, DERIVED=1>": "_ZN5chimp21twoPhaseCollideKernelINS_5D3Q19ELb0ELi1ELb1EEEvNS_12TwoPhaseArgsE",
+    "two-phase collide pass, full phi table  twoPhaseCollideKernel<D3Q19, MOM=0, IDX_COMPACT, DERIVED=0>": "_ZN5chimp21twoPhaseCollideKernelINS_5D3Q19ELb0ELi1ELb0EEEvNS_12TwoPhaseArgsE",
 }
 HEADER = """# r02: SASS of the step kernels (cuobjdump -sass / -res-usage of badchimp-cpp_b200/libchimp_b200.so, sm_100a, nvcc 12.9,
 # -O3 -fmad=false -lineinfo; scripts/sass_summary.py).  Opcode histogram, resources, and the instructions that touch global memory.
