@@ -141,7 +141,7 @@ def _drained(fn):
     return wrapper
 
 
-for _name in ("all_reduce", "all_gather", "all_gather_object", "gather_object", "barrier", "batch_isend_irecv", "broadcast",
-              "send", "recv", "isend", "irecv"):
+# (isend / irecv themselves stay untouched: P2POp compares them by identity)
+for _name in ("all_reduce", "all_gather", "all_gather_object", "gather_object", "barrier", "batch_isend_irecv", "broadcast"):
     if hasattr(_dist, _name):
         setattr(_dist, _name, _drained(getattr(_dist, _name)))
