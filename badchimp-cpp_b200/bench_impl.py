@@ -215,7 +215,8 @@ class _Runner:
         return self.lat.step_timed(k, tau=self.wl["tau"], force=self.wl["force"], trt=self.wl["trt"])
 
 
-def parity_probe(pkg, ingest, multi, wl, workload, rank, world, device, index_form, halo, interior_domains, steps=10, size=None):
+def parity_probe(pkg, ingest, multi, wl, workload, rank, world, device, index_form, halo, interior_domains, steps=10, size=None,
+                 skip_mask=False):
     """A small case of the same workload on the same code path (structured ingest, N z-slabs, the same halo
     transport and step kernels) checked against the oracle port of the UNDECOMPOSED geometry on rank 0's host,
     before anything is timed: after one step (the per-step bar: bit-exact for the single-field kernels, <= 1e-12
@@ -232,6 +233,8 @@ def parity_probe(pkg, ingest, multi, wl, workload, rank, world, device, index_fo
             size = 4 * world
     rl = W.build(pkg, ingest, multi, wl, size, rank, world, device, scaling, index_form, halo=halo, balance=True,
                  interior_domains=interior_domains, keep_cells=True)
+    if skip_mask:
+        rl.lat.set_index_skip_mask(True)
     run = _Runner(rl, wl)
     stages = [1, steps]
     payloads, done = [], 0
@@ -336,9 +339,10 @@ def _ncu_traffic(args):
     # the child steps two at a time: launch 0 of a pair is a step without the moment output (like all timed steps but the last)
     count = "2" if args.workload == "twophase" else "1"
     skip = "4" if args.workload == "twophase" else "2"
-    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none", "--print-units", "base", "-k", kern,
+    cmd = ([ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none", "--print-units", "base", "-k", kern,
            "--launch-skip", skip, "--launch-count", count, "--csv", sys.executable, bench, "--traffic-probe", "--workload", args.workload,
-           "--index", args.index, "--size", str(args.size or 0)] + (["--interior-domains"] if args.interior_domains else [])
+           "--index", args.index, "--size", str(args.size or 0), "--skip-mask", "on" if getattr(args, "skip_mask_selected", False) else "off"] +
+          (["--interior-domains"] if args.interior_domains else []))
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
         read = write = 0.0
@@ -379,6 +383,8 @@ def run_traffic_probe(args):
     index_form = pkg.capi.INDEX_COMPACT if args.index == "compact" else pkg.capi.INDEX_TABLE
     rl = W.build(pkg, ingest, multi, wl, args.size or wl["size"], 0, 1, torch.device("cuda", 0), "strong", index_form,
                  interior_domains=args.interior_domains)
+    if args.skip_mask == "on":
+        rl.lat.set_index_skip_mask(True)
     run = _Runner(rl, wl)
     for _ in range(3):
         run.step(2)     # per call: one step without and one with the moment output (rho, vel) of the last step
@@ -460,13 +466,46 @@ def _e2e_from_init_rho(pkg, rl, wl, run, steps, device):
             "cycle": "upload init_rho (pinned host ScalarField) + f = w_q rho on the device + %d steps + download rho, vel; wall clock; one untimed cycle before" % steps}
 
 
-def _measure(pkg, rl, wl, args, total, barrier, rank, sample_clocks):
-    """warm-up, K timed steps (CUDA events on the engine's stream, max over ranks), clocks under load"""
+def _try_skip_mask(pkg, ingest, multi, rl, wl, run, args, workload, device, index_form):
+    """One GPU, compact index, plain single-field step: the skip-mask kernel form (chimp_set_index_skip_mask) reads fewer
+    index bytes behind one more dependent load, so which form is faster is measured -- a few untimed steps of each after
+    the warm-up -- and the winner has to pass its own parity probe before it is timed.  Rank-local; everything is
+    reported (config.index_skip_mask); a failure costs the form, not the line."""
+    if wl["physics"] != "single" or args.index != "compact" or args.skip_mask == "off":
+        return None
+    info = {"skipped_word_share": rl.lat.index_skipped_word_fraction(), "mode": args.skip_mask}
+    try:
+        if args.skip_mask == "auto":
+            trial = max(5, min(args.steps, 20))
+            for _ in range(2):          # the second round counts: both forms have run once by then
+                rl.lat.set_index_skip_mask(False)
+                t_plain = run.timed(trial) / trial
+                rl.lat.set_index_skip_mask(True)
+                t_mask = run.timed(trial) / trial
+            info["trial_ms_per_step"] = {"plain": t_plain, "skip_mask": t_mask, "steps_each": trial}
+            selected = t_mask < t_plain
+        else:
+            selected = True
+        if selected:
+            info["parity"] = parity_probe(pkg, ingest, multi, wl, workload, 0, 1, device, index_form, args.halo, False, skip_mask=True)
+        rl.lat.set_index_skip_mask(selected)
+        info["selected"] = "skip_mask" if selected else "plain"
+    except BaseException as exc:
+        rl.lat.set_index_skip_mask(False)
+        info["selected"] = "plain"
+        info["error"] = str(exc)[:300]
+    return info
+
+
+def _measure(pkg, rl, wl, args, total, barrier, rank, sample_clocks, choose_form=None):
+    """warm-up, K timed steps (CUDA events on the engine's stream, max over ranks), clocks under load.  choose_form: called
+    between the warm-up and the timed region (one GPU: trial of the index forms, untimed)"""
     import torch
     capi = pkg.capi
     run = _Runner(rl, wl)
     run.step(args.warmup)
     rl.lat.synchronize()
+    form = choose_form(run) if choose_form else None
     samples, stop = [], threading.Event()
     th = threading.Thread(target=_clock_sampler, args=(stop, samples), daemon=True)
     if sample_clocks and rank == 0:
@@ -497,7 +536,7 @@ def _measure(pkg, rl, wl, args, total, barrier, rank, sample_clocks):
         rl.lat.download_rho(r2)
         rho_sum = r2[1:].sum()
     mass_err = abs(total(float(rho_sum), "sum") / total(rl.n, "sum") - 1.0)
-    return dict(ms=ms, ms_max=ms_max, launches=int(l2 - l1), samples=samples, mass_err=mass_err, run=run)
+    return dict(ms=ms, ms_max=ms_max, launches=int(l2 - l1), samples=samples, mass_err=mass_err, run=run, form=form)
 
 
 def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, peak):
@@ -513,6 +552,7 @@ def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, p
         run = _Runner(rl, wl)
         run.step(max(args.warmup, 3))
         rl.lat.synchronize()
+        form = None if rl is main_rl else _try_skip_mask(pkg, ingest, multi, rl, wl, run, args, name.split("+")[0], device, index_form)
         ms = run.timed(args.steps)
         rl.lat.synchronize()
         n = rl.n
@@ -521,6 +561,8 @@ def _extra_workloads(pkg, ingest, multi, W, main_rl, args, device, index_form, p
              "ms_per_step": ms / args.steps, "value": n * args.steps / (ms * 1e-3) / 1e6, "unit": "MLUPS",
              "roofline": {"bytes_per_node": wl["b_alg"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
              "index_bytes_per_node": rl.lat.index_bytes_per_node(), "irregular_tile_fraction": rl.lat.irregular_fraction()}
+        if form:
+            e["index_skip_mask"] = form
         if rl.lat.n_fields == 2:
             e["phi_index_bytes_per_node"] = rl.lat.phi_index_bytes_per_node()
         if wl["physics"] == "one_phase":
@@ -658,7 +700,14 @@ def run_b200(args):
     rl = W.build(pkg, ingest, multi, wl, size, rank, world, device, scaling, index_form, halo=args.halo, balance=args.balance,
                  interior_domains=args.interior_domains)
     setup_s = time.perf_counter() - t_setup
-    m = _measure(pkg, rl, wl, args, total, barrier, rank, True)
+    def choose_form(run):
+        if world != 1:
+            return None
+        info = _try_skip_mask(pkg, ingest, multi, rl, wl, run, args, args.workload, device, index_form)
+        args.skip_mask_selected = bool(info) and info.get("selected") == "skip_mask"
+        return info
+
+    m = _measure(pkg, rl, wl, args, total, barrier, rank, True, choose_form)
     n_total = total(rl.n, "sum")
     per_rank = None
     if world > 1:
@@ -725,6 +774,8 @@ def run_b200(args):
                   "l2_policy": "state per GPU 2 x %.2f GB >> 126 MB L2 (inputs larger than L2)" % (n_total / world * b_alg / 2 / 1e9),
                   "irregular_tile_fraction": irregular, "index_bytes_per_node": index_bytes, "setup_seconds": setup_s,
                   "mean_rho_error": m["mass_err"]}
+        if m.get("form"):
+            config["index_skip_mask"] = m["form"]
         if phi_index_bytes is not None:
             config["phi_index_bytes_per_node"] = phi_index_bytes
         if attr_bytes is not None:

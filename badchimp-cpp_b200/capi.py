@@ -51,7 +51,7 @@ SYMBOLS = [
     "chimp_num_neighbors", "chimp_neighbor_info", "chimp_send_buffer_dev", "chimp_recv_buffer_dev",
     "chimp_set_exchange_callback", "chimp_set_stream", "chimp_synchronize", "chimp_num_own_nodes",
     "chimp_host_table_info", "chimp_host_table", "chimp_host_halo_lists", "chimp_host_constant_links", "chimp_irregular_fraction",
-    "chimp_index_bytes_per_node", "chimp_phi_index_bytes_per_node", "chimp_one_phase_attribute_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_step_twophase_timed", "chimp_peer_mode", "chimp_voxel_table_host", "chimp_create_from_voxels",
+    "chimp_index_bytes_per_node", "chimp_phi_index_bytes_per_node", "chimp_set_index_skip_mask", "chimp_index_skipped_word_fraction", "chimp_one_phase_attribute_bytes_per_node", "chimp_plane_stride", "chimp_step_timed", "chimp_step_twophase_timed", "chimp_peer_mode", "chimp_voxel_table_host", "chimp_create_from_voxels",
     "chimp_voxel_phi_table_host", "chimp_set_phi_table_from_voxels", "chimp_slab_tables_host", "chimp_create_slab_from_voxels",
     "chimp_halo_face_recv_count", "chimp_halo_face_recv_list", "chimp_init_uniform",
     "chimp_download_moments_device_order", "chimp_step_begin", "chimp_step_end", "chimp_download_mass_change",
@@ -76,6 +76,8 @@ def lib():
         l.chimp_irregular_fraction.argtypes = [C.c_void_p]
         l.chimp_index_bytes_per_node.restype = C.c_double
         l.chimp_index_bytes_per_node.argtypes = [C.c_void_p]
+        l.chimp_index_skipped_word_fraction.restype = C.c_double
+        l.chimp_index_skipped_word_fraction.argtypes = [C.c_void_p]
         l.chimp_one_phase_attribute_bytes_per_node.restype = C.c_double
         l.chimp_one_phase_attribute_bytes_per_node.argtypes = [C.c_void_p]
         l.chimp_phi_index_bytes_per_node.restype = C.c_double
@@ -534,6 +536,13 @@ class Lattice:
 
     def index_bytes_per_node(self):
         return float(lib().chimp_index_bytes_per_node(self.h))
+
+    def set_index_skip_mask(self, on=True):
+        """compact index, plain single-field step: kernel form that skips the delta words marked as plain runs"""
+        _check(lib().chimp_set_index_skip_mask(self.h, C.c_int(1 if on else 0)))
+
+    def index_skipped_word_fraction(self):
+        return float(lib().chimp_index_skipped_word_fraction(self.h))
 
     def one_phase_attribute_bytes_per_node(self):
         """one_phase lattices: 4 = attributes packed into one word per node, 24 = four arrays"""

@@ -28,6 +28,7 @@
 namespace chimp {
 __global__ void fillKernel(double *p, double v, long long count);
 __global__ void classifyTilesKernel(const int32_t *, int, int, int, int, int32_t *, uint8_t *, int *);
+__global__ void skipMaskKernel(const uint32_t *, int, int, int, int, int32_t *, unsigned long long *);
 __global__ void fillRowsKernel(const int32_t *, int, int, int, int, const int32_t *, int32_t *, int, long long);
 __global__ void kernelTableKernel(const int32_t *, int32_t *, int, int, int, int, long long);
 } // namespace chimp
@@ -151,6 +152,8 @@ struct chimp_lattice {
     int labelMin = 0, labelMax = -1;
     bool labelsContiguous = false;
     uint32_t *d_delta = nullptr, *d_pmask = nullptr;
+    bool skipMask = false;              // single-field step kernel in IDX_COMPACT_MASK form (chimp_set_index_skip_mask)
+    unsigned long long skippedWords = 0; // (tile, delta word) pairs that form skips
     uint32_t *d_attr = nullptr; // one_phase attributes packed into one word per node (kernels.cuh, StepArgs::attr), if they pack
     bool attrPackEnv = true;
     int nWords = 0;
@@ -323,6 +326,17 @@ int buildRankIndex(chimp_lattice *c)
     CUDA_OK(cudaStreamSynchronize(c->stream));
     cudaFree(d_cnt);
     c->nRows = cnt;
+    {   // skip mask of the delta words (IDX_COMPACT_MASK): always built, it lives in a slot the plain compact form never reads
+        unsigned long long *d_skipped = nullptr;
+        CUDA_OK(cudaMalloc(&d_skipped, sizeof(unsigned long long)));
+        CUDA_OK(cudaMemsetAsync(d_skipped, 0, sizeof(unsigned long long), c->stream));
+        skipMaskKernel<<<(unsigned)((c->nTiles + 127) / 128), 128, 0, c->stream>>>(c->d_delta, c->n, c->nPad, nQ, c->nTiles, c->d_base, d_skipped);
+        ++g_launches;
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpyAsync(&c->skippedWords, d_skipped, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        cudaFree(d_skipped);
+    }
     CUDA_OK(cudaMalloc(&c->d_rows, (size_t)std::max(cnt, 1) * 32 * sizeof(int32_t)));
     if (cnt > 0) {
         fillRowsKernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->n, c->nPad, nQ, c->nTiles, c->d_base, c->d_rows, c->li.nPairs, c->stride);
@@ -369,7 +383,10 @@ void dispatchSingle(const chimp_lattice *c, const StepArgs &a, int coll, bool mo
     const bool rk = c->indexForm == CHIMP_INDEX_COMPACT;
 #define CH_LAUNCH(COLL, OP, IDX) launchSingle<L, COLL, OP, IDX>(a, mom, s)
 #define CH_INDEX(COLL, OP) do { if (rk) CH_LAUNCH(COLL, OP, IDX_COMPACT); else CH_LAUNCH(COLL, OP, IDX_TABLE); } while (0)
-#define CH_ATTR(COLL) do { if (op == OP_PACKED) CH_INDEX(COLL, OP_PACKED); else if (op == OP_ARRAYS) CH_INDEX(COLL, OP_ARRAYS); else CH_INDEX(COLL, OP_NONE); } while (0)
+    // the skip-mask form exists for the plain single-field kernel outside the fused peer launch
+    const bool masked = rk && c->skipMask && op == OP_NONE && a.peer.blocks == 0;
+#define CH_ATTR(COLL) do { if (masked) CH_LAUNCH(COLL, OP_NONE, IDX_COMPACT_MASK); else if (op == OP_PACKED) CH_INDEX(COLL, OP_PACKED); \
+                           else if (op == OP_ARRAYS) CH_INDEX(COLL, OP_ARRAYS); else CH_INDEX(COLL, OP_NONE); } while (0)
     if (coll == CHIMP_BGK) CH_ATTR(COLL_BGK);
     else CH_ATTR(COLL_TRT);
 #undef CH_ATTR
@@ -2283,6 +2300,12 @@ void preloadStepKernels(bool twoField)
     preloadOnePhaseForms<L, IDX, OP_NONE>();
     preloadOnePhaseForms<L, IDX, OP_ARRAYS>();
     preloadOnePhaseForms<L, IDX, OP_PACKED>();
+    if constexpr (IDX == IDX_COMPACT) {
+        preloadKernel(collideStreamKernel<L, COLL_BGK, OP_NONE, false, IDX_COMPACT_MASK>);
+        preloadKernel(collideStreamKernel<L, COLL_BGK, OP_NONE, true, IDX_COMPACT_MASK>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, OP_NONE, false, IDX_COMPACT_MASK>);
+        preloadKernel(collideStreamKernel<L, COLL_TRT, OP_NONE, true, IDX_COMPACT_MASK>);
+    }
     preloadKernel(massChangeKernel<L, IDX>);
     if constexpr (L::id != D3Q27::id) {
         if (twoField) {
@@ -2932,7 +2955,21 @@ double chimp_index_bytes_per_node(chimp_lattice *c)
 {
     if (!c || c->n == 0) return 0.0;
     if (c->indexForm == CHIMP_INDEX_TABLE) return 4.0 * c->li.nQ;
-    return (4.0 * c->nWords * c->nPad + 16.0 * c->nTiles * c->nWords + 128.0 * c->nRows) / c->n;
+    // delta words (minus the skipped ones when the skip-mask form is on) + bases + explicit rows
+    const double skipped = c->skipMask && !c->onePhase ? 128.0 * (double)c->skippedWords : 0.0;
+    return (4.0 * c->nWords * c->nPad - skipped + 16.0 * c->nTiles * c->nWords + 128.0 * c->nRows) / c->n;
+}
+int chimp_set_index_skip_mask(chimp_lattice *c, int on)
+{
+    if (check(c, true)) return 1;
+    if (on && c->indexForm != CHIMP_INDEX_COMPACT) return fail("the skip mask belongs to the compact index form");
+    c->skipMask = on != 0;
+    return 0;
+}
+double chimp_index_skipped_word_fraction(chimp_lattice *c)
+{
+    if (!c || c->indexForm != CHIMP_INDEX_COMPACT || c->nTiles == 0) return 0.0;
+    return (double)c->skippedWords / ((double)c->nTiles * c->nWords);
 }
 double chimp_one_phase_attribute_bytes_per_node(chimp_lattice *c)
 {

@@ -236,6 +236,31 @@ __global__ void classifyTilesKernel(const int32_t *__restrict__ table, int n, in
     }
 }
 
+// Skip mask of IDX_COMPACT_MASK, one thread per tile: bit w of the tile's spare base slot (4 NW - 1, never a direction)
+// is set when every live lane of the tile has byte == lane in all directions of delta word w -- the sources of those
+// directions are 32 consecutive slots starting at the base, and the step kernel need not read the word.
+__global__ void skipMaskKernel(const uint32_t *__restrict__ delta, int n, int nPad, int nQ, int nTiles, int32_t *__restrict__ base,
+                               unsigned long long *skippedWords)
+{
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= nTiles) return;
+    const int nW = (nQ + 3) / 4, nSlots = nW * 4;
+    unsigned mask = 0;
+    for (int w = 0; w < nW; ++w) {
+        const int dirs = min(4, nQ - 4 * w);                       // the last word may hold fewer than four directions
+        const uint32_t cmp = dirs == 4 ? 0xffffffffu : ((1u << (8 * dirs)) - 1u);
+        bool run = true;
+        for (int lane = 0; lane < 32 && run; ++lane) {
+            const int i = tile * 32 + lane;
+            if (i >= n) break;
+            run = ((delta[(long long)w * nPad + i] ^ ((uint32_t)lane * 0x01010101u)) & cmp) == 0u;
+        }
+        if (run) mask |= 1u << w;
+    }
+    base[(long long)tile * nSlots + nSlots - 1] = (int32_t)mask;
+    if (mask) atomicAdd(skippedWords, (unsigned long long)__popc(mask));
+}
+
 // kernel form of the pull table: -1 (reversed own slot) becomes i + (rev q - q) * stride
 __global__ void kernelTableKernel(const int32_t *__restrict__ table, int32_t *__restrict__ ktable, int n, int nPad,
                                   int nQ, int nPairs, long long stride)

@@ -48,7 +48,10 @@ namespace chimp {
 enum { COLL_BGK = 0, COLL_TRT = 1 };
 // one_phase variant of the single-field kernel: per-node attributes from four arrays (24 B/node) or from one packed word
 enum { OP_NONE = 0, OP_ARRAYS = 1, OP_PACKED = 2 };
-enum { IDX_TABLE = 0, IDX_COMPACT = 1 };
+// IDX_COMPACT_MASK reads the tables of IDX_COMPACT; the spare base slot of a tile additionally says which of its delta
+// words are plain runs (byte == lane for every live lane: the sources of those four directions are 32 consecutive slots),
+// and such words are not read.  Only the single-field step kernel has this form (chimp_set_index_skip_mask).
+enum { IDX_TABLE = 0, IDX_COMPACT = 1, IDX_COMPACT_MASK = 2 };
 
 // The step kernels address one plane as  in[q] + s  with a signed 32-bit slot index s.  A bounce
 // (reversed own slot X[rev q][i]) is expressed in the same form: s = i + (rev q - q) * stride,
@@ -177,6 +180,38 @@ __device__ __forceinline__ void resolveSources(const Args &a, int i, bool live, 
     if (IDX == IDX_TABLE) {
 #pragma unroll
         for (int q = 0; q < L::nQ; ++q) s[q] = live ? __ldg(a.idx.table + ((unsigned)q * (unsigned)a.nPad + (unsigned)i)) : 0;
+    } else if (IDX == IDX_COMPACT_MASK) {
+        constexpr int NW = (L::nQ + 3) / 4;
+        const int tile = min(i >> 5, a.idx.nTiles - 1);
+        // the tile's bases first: their spare slot (never a direction: 4 NW > nQ) holds the skip mask of the delta words
+        const int4 *bp = reinterpret_cast<const int4 *>(a.idx.base) + (unsigned)tile * NW;
+        int base[NW * 4];
+#pragma unroll
+        for (int g = 0; g < NW; ++g) {
+            const int4 v = __ldg(bp + g);
+            base[4 * g] = v.x; base[4 * g + 1] = v.y; base[4 * g + 2] = v.z; base[4 * g + 3] = v.w;
+        }
+        const uint32_t skip = (uint32_t)base[NW * 4 - 1];
+        const uint32_t run = (threadIdx.x & 31u) * 0x01010101u; // byte == lane in all four directions of a word
+        uint32_t wd[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            wd[w] = ((skip >> w) & 1u) ? run : (live ? __ldg(a.idx.delta + ((unsigned)w * (unsigned)a.nPad + (unsigned)i)) : 0u);
+        int anyRow = 0;
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) {
+            const int d = (int)((wd[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            s[q] = (d == 255) ? i + a.idx.bounceOff[q] : base[q] + d;
+            anyRow |= base[q];
+        }
+        if (anyRow < 0) { // warp-uniform and rare: some (tile, q) of this tile keeps an explicit row
+            const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+            for (int q = 0; q < L::nQ; ++q)
+                if (base[q] < 0) s[q] = __ldg(a.idx.rows + (((unsigned)(-base[q] - 1) << 5) + lane));
+        }
+#pragma unroll
+        for (int q = 0; q < L::nQ; ++q) s[q] = live ? s[q] : 0;
     } else {
         constexpr int NW = (L::nQ + 3) / 4;
         const int tile = min(i >> 5, a.idx.nTiles - 1);
@@ -243,7 +278,7 @@ __global__ void __launch_bounds__(CHIMP_BLOCK, CHIMP_MIN_BLOCKS) collideStreamKe
     const bool peerBlock = PEER && (int)blockIdx.x < a.peer.blocks;
     if (!peerBlock) {
         if (IDX == IDX_TABLE && !live) return;
-        if (IDX == IDX_COMPACT && (i & ~31) >= a.end) return; // whole warp out of range
+        if (IDX != IDX_TABLE && (i & ~31) >= a.end) return; // whole warp out of range
     }
     uint32_t sendMask = 0;
     if (PEER && peerBlock) {

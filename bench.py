@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size", type=int, default=0, help="edge length of the cubic sphere pack (0 = default)")
     ap.add_argument("--index", default="compact", choices=["compact", "table"])
+    ap.add_argument("--skip-mask", default="auto", choices=["auto", "on", "off"],
+                    help="N=1, compact index, plain single-field step: kernel form that skips the delta words marked as plain runs; "
+                         "auto = both forms are tried for a few untimed steps after the warm-up and the faster one is timed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="std_case", choices=["std_case", "trt", "one_phase", "d2q9_channel", "twophase", "d3q27_dense"])
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N>1: split one lattice (strong) or one block per GPU (weak); default per workload")

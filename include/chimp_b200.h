@@ -303,6 +303,13 @@ int chimp_num_own_nodes(chimp_lattice *);
 double chimp_irregular_fraction(chimp_lattice *);
 /* device bytes of index data read per node per step, and of population data */
 double chimp_index_bytes_per_node(chimp_lattice *);
+/* Compact index, plain single-field step (no one_phase attributes, outside the fused peer launch): on != 0 selects the
+ * kernel form that first reads a tile's bases and skips every delta word the tile's skip mask marks as a plain run
+ * (byte == lane: the sources of those four directions are 32 consecutive slots).  Same tables, same results; fewer index
+ * bytes (chimp_index_bytes_per_node follows) behind one more dependent load.  Off by default; bench.py tries both forms
+ * before it times.  chimp_index_skipped_word_fraction: share of the (tile, delta word) pairs that are such runs. */
+int chimp_set_index_skip_mask(chimp_lattice *, int on);
+double chimp_index_skipped_word_fraction(chimp_lattice *);
 /* one_phase lattices: bytes per node and step of the per-node attributes the step kernel reads (force switch, source
  * switch, interior label, link mask): 4 when they pack into one word (switches exactly 0 / 1, at most 16 labels;
  * CHIMP_ATTR_PACKED=0 keeps the arrays), 24 as four arrays, 0 before chimp_set_one_phase_attributes */

@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "badchimp-cpp_b200", "libchimp_b200.so")
 KERNELS = {
     "default single-GPU step kernel  collideStreamKernel<D3Q19, BGK, ONEPHASE=0, MOM=0, IDX_COMPACT, PEER=0>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELi0ELb0ELi1ELb0EEEvNS_8StepArgsE",
+    "step kernel, skip-mask form of the compact index (untimed variant; bench.py tries it against the default before timing)  collideStreamKernel<D3Q19, BGK, 0, 0, IDX_COMPACT_MASK, 0>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELi0ELb0ELi2ELb0EEEvNS_8StepArgsE",
     "N-GPU step kernel (peer exchange fused)  collideStreamKernel<D3Q19, BGK, 0, 0, IDX_COMPACT, PEER=1>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi0ELi0ELb0ELi1ELb1EEEvNS_8StepArgsE",
     "one_phase step kernel, packed attribute word (untimed variant)  collideStreamKernel<D3Q19, TRT, OP_PACKED, 0, IDX_COMPACT, 0>": "_ZN5chimp19collideStreamKernelINS_5D3Q19ELi1ELi2ELb0ELi1ELb0EEEvNS_8StepArgsE",
     "two-phase collide pass, derived phi index (untimed variant)  twoPhaseCollideKernel<D3Q19, MOM=0, IDX_COMPACT, DERIVED=1>": "_ZN5chimp21twoPhaseCollideKernelINS_5D3Q19ELb0ELi1ELb1EEEvNS_12TwoPhaseArgsE",

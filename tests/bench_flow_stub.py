@@ -47,6 +47,8 @@ class FakeLat:
     def download(self): return np.zeros((self.n_nodes, self.n_fields, self.nq))
     def irregular_fraction(self): return 0.01
     def index_bytes_per_node(self): return 23.5
+    def set_index_skip_mask(self, on=True): self.skip = bool(on)
+    def index_skipped_word_fraction(self): return 0.6
     def phi_index_bytes_per_node(self): return 6.0
     def one_phase_attribute_bytes_per_node(self): return 4.0
     def peer_mode(self): return (2, "")
@@ -108,7 +110,7 @@ def main():
     args.workload = os.environ.get("WL", "std_case")
     args.scaling, args.size, args.index, args.halo, args.balance = None, 0, "compact", "peer", True
     args.interior_domains, args.no_parity, args.no_weak, args.no_traffic, args.no_cpu_baseline, args.no_extra_workloads = False, False, False, False, False, False
-    args.steps, args.warmup, args.gpus = 20, 5, world
+    args.steps, args.warmup, args.gpus, args.skip_mask = 20, 5, world, "auto"
     bench_impl.run_b200(args)
 
 main()
